@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures in tests/golden/ from the UNMODIFIED v1 reference.
+
+Run in the build container only (needs /root/reference):
+
+    bash oracle/build_ref.sh && python tests/golden/make_golden.py
+
+The reference has no tests and no golden vectors of its own, so its runnable
+generation (old/*, compiled by oracle/build_ref.sh with -O2 and no fast-math) is executed here
+and its outputs are frozen.  The fixtures are what pins oracle/rt_oracle.c, and through it the
+CUDA path, to the reference:
+
+  default9_primary.npz     default 9-sphere scene (interaction.py:294-355), camera
+                           interaction.py:640-643, 640x480, pixel centres, Scene::hit(0.001,1e10):
+                           full object-id image, per-id histogram, distances on a 4x4 lattice and
+                           on the ground sphere's horizon rows, centre-ray record
+  spheres1000_primary.npz  1000 random spheres, 200x150: ids + distances (BVH path)
+  spheres1000_rays.npz     4096 incoherent rays through Scene::hit on the same scene
+  camera_rays.npz          Camera::get_ray for three cameras on a 9x9 (u,v) grid
+  select_object.npz        RayTracer::select_object on a 16x12 click grid (default scene)
+  default9_v1_images.npz   RayTracer::render at 160x120: 4096 spp depth 4, 2048 spp depth 2,
+                           2048 spp depth 1 (v1's RNG is random_device-seeded mt19937, so these are
+                           statistical references: compare by RMSE/PSNR, not bit-wise)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_v1  # noqa: E402
+from pgr_raytracing_project_b200 import scenes  # noqa: E402
+
+
+def fnv1a64(ids: np.ndarray) -> int:
+    h = 0xCBF29CE484222325
+    for v in (ids.ravel().astype(np.int64) + 1).tolist():
+        h = ((h ^ (v & 0xFFFFFFFF)) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def main():
+    assert ref_v1.available("strict"), "run oracle/build_ref.sh first"
+    s = scenes.default_scene()
+    W, H = 640, 480
+    cam = s.camera.as_array(W / H)
+    rs = ref_v1.RefScene(s.center_radius, s.material8, s.object_id, s.background)
+    ids, t, nrm, _ = rs.primary(cam, W, H, want_normals=True)
+    brute = ref_v1.RefScene(s.center_radius, s.material8, s.object_id, s.background, use_bvh=False)
+    ids_b, t_b, _, _ = brute.primary(cam, W, H)
+    assert np.array_equal(ids, ids_b)
+    o, d = ref_v1.camera_get_ray(cam, 0.5, 0.5)
+    cid, ct = rs.hit_rays(o[None], d[None])
+    hist = np.array([(ids == k).sum() for k in range(-1, 9)], dtype=np.int64)
+    horizon = slice(150, 164)
+    np.savez_compressed(
+        os.path.join(HERE, "default9_primary.npz"),
+        width=W, height=H, cam=cam, ids=ids.astype(np.int8), hist=hist,
+        t_lattice=t[::4, ::4], t_horizon=t[horizon], horizon_rows=np.array([150, 164]),
+        normal_lattice=nrm[::8, ::8].astype(np.float32),
+        sum_t=np.float64(t[ids >= 0].sum()), fnv1a64=np.uint64(fnv1a64(ids)),
+        centre_dir=d, centre_id=cid[0], centre_t=ct[0])
+    print("default9:", dict(zip(range(-1, 9), hist.tolist())), "sum_t", t[ids >= 0].sum(), "centre t", ct[0])
+
+    s2 = scenes.random_spheres(1000, seed=7, extent=4.0, rmin=0.05, rmax=0.3, cam_z=12.0)
+    W2, H2 = 200, 150
+    cam2 = s2.camera.as_array(W2 / H2)
+    r2 = ref_v1.RefScene(s2.center_radius, s2.material8, s2.object_id, s2.background)
+    ids2, t2, _, _ = r2.primary(cam2, W2, H2)
+    np.savez_compressed(os.path.join(HERE, "spheres1000_primary.npz"), width=W2, height=H2, cam=cam2,
+                        seed=7, ids=ids2.astype(np.int16), t=t2)
+    rng = np.random.default_rng(99)
+    org = rng.uniform(-6, 6, size=(4096, 3)).astype(np.float32)
+    tgt = rng.uniform(-3, 3, size=(4096, 3)).astype(np.float32)
+    dirs = (tgt - org).astype(np.float32)
+    idr, tr = r2.hit_rays(org.astype(np.float64), dirs.astype(np.float64))
+    np.savez_compressed(os.path.join(HERE, "spheres1000_rays.npz"), org=org, dir=dirs, ids=idr.astype(np.int16), t=tr)
+    print("spheres1000: hit fraction", (ids2 >= 0).mean(), "rays hit fraction", (idr >= 0).mean())
+
+    cams = [cam, scenes.cornell_box().camera.as_array(1.0),
+            ref_v1.cam_array((3.0, 1.0, -2.0), (0.0, 0.5, -3.0), fov=60.0, aspect=16 / 9)]
+    uv = np.linspace(0.0, 1.0, 9)
+    rays = np.zeros((len(cams), 9, 9, 3))
+    for k, c in enumerate(cams):
+        for a, v in enumerate(uv):
+            for b, u in enumerate(uv):
+                rays[k, a, b] = ref_v1.camera_get_ray(c, u, v)[1]
+    np.savez_compressed(os.path.join(HERE, "camera_rays.npz"), cams=np.array(cams), uv=uv, dirs=rays)
+
+    clicks = np.array([[(i + 0.5) / 16, (j + 0.5) / 12] for j in range(12) for i in range(16)])
+    sel = np.array([rs.select_object(cam, x, y, W, H) for x, y in clicks], dtype=np.int32)
+    np.savez_compressed(os.path.join(HERE, "select_object.npz"), cam=cam, clicks=clicks, ids=sel)
+
+    Wi, Hi = 160, 120
+    cami = s.camera.as_array(Wi / Hi)
+    img4, _ = rs.render(cami, Wi, Hi, 4096, 4)
+    img2, _ = rs.render(cami, Wi, Hi, 2048, 2)
+    img1, _ = rs.render(cami, Wi, Hi, 2048, 1)
+    np.savez_compressed(os.path.join(HERE, "default9_v1_images.npz"), width=Wi, height=Hi, cam=cami,
+                        depth4_4096spp=img4.astype(np.float32), depth2_2048spp=img2.astype(np.float32),
+                        depth1_2048spp=img1.astype(np.float32))
+    print("images: means", img4.mean((0, 1)), img2.mean((0, 1)), img1.mean((0, 1)))
+
+
+if __name__ == "__main__":
+    main()
