@@ -1,0 +1,159 @@
+/* b200rt.h -- C ABI of libb200rt.so, the B200-native (sm_100a CUDA) replacement for the render
+ * hot path of Samuel-2000/PGR-Raytracing-Project: camera ray generation -> BVH traversal with
+ * ray/primitive intersection -> path-traced shading -> sample accumulation / resolve.
+ *
+ * This is exactly what a binding for the reference's native module `cpp_raytracer.raytracer_cpp`
+ * has to bind for that path (INTEGRATION.md shows the pybind11 and ctypes stubs).  Each entry
+ * point names the reference interface it replaces; paths are relative to the reference root,
+ * "v1" = old/ * (the generation that compiles and runs, and the API interaction.py is written
+ * against), "v2" = cpp_raytracer/raytracer_core.{h,cpp}.
+ *
+ * Conventions: every call returns 0 on success, non-zero on failure (rt_last_error gives the
+ * text); nothing throws across the boundary.  Pointers prefixed d_ are DEVICE pointers owned by
+ * the caller (e.g. a torch CUDA tensor's data_ptr()); h_ are HOST pointers; scene / BVH device
+ * memory is owned by the context.  `stream` is a cudaStream_t passed as void* (NULL = the
+ * legacy default stream); calls that take a stream only enqueue work on it.  A context is
+ * internally locked: calls on one context from different host threads serialise
+ * (gui.py:943,957,981 call set_scene while the render worker may be inside render).
+ * There is NO CPU fallback: without a CUDA device rt_create fails.
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RT_ABI_VERSION 1
+
+typedef struct rt_ctx rt_ctx;
+
+/* Flattened BVH node, 32 bytes, read on the device as two 16-byte vector loads.
+ * Replaces v2 BVHNodeFlat (cpp_raytracer/raytracer_core.h:221-235, 96 bytes, leaf flag aliased
+ * with a child index) and v1's pointer BVHNode (old/bvh copy.h:26-39).
+ *   internal node: b == 0, a = index of the left child; the right child is a + 1 (siblings are
+ *                  adjacent and 64-byte aligned: a is even);
+ *   leaf node:     b = primitive count (1..4), a = first slot into the leaf-ordered primitive
+ *                  arrays (prim_index[slot] = primitive number in upload order).
+ * Node 0 is the root, node 1 is an unused pad record. */
+typedef struct rt_bvh_node {
+    float bmin[3];
+    int32_t a;
+    float bmax[3];
+    int32_t b;
+} rt_bvh_node;
+
+/* Counters for the roofline; filled only while option "stats" is 1. */
+typedef struct rt_stats {
+    uint64_t rays;          /* camera samples (render) or rays (trace_*) */
+    uint64_t segments;      /* path segments traced (== rays for primary-only work) */
+    uint64_t node_records;  /* 32-byte node records fetched */
+    uint64_t prim_tests;    /* primitives tested (48 B per triangle, 16 B per sphere) */
+    uint64_t launches;      /* kernels launched by this context since creation / reset */
+} rt_stats;
+
+/* ---- context: replaces RayTracer::RayTracer / ~RayTracer (old/raytracer_core copy.cpp:148-160) */
+int rt_create(int device, rt_ctx** out);
+void rt_destroy(rt_ctx* ctx);
+const char* rt_last_error(rt_ctx* ctx);          /* ctx may be NULL (errors of rt_create) */
+int rt_abi_version(void);
+
+/* ---- scene upload: replaces RayTracer::set_scene (old/raytracer_core copy.cpp:162-167; v2
+ * RayTracerWrapper::set_scene raytracer_core.cpp:542-547) which deep-copies the sphere list.
+ * center_radius: n x 4 (cx cy cz r); material8: n x 8 (albedo3 metallic roughness emission3,
+ * i.e. Material old/raytracer_core copy.h:110-119 without the never-read ior); object_id may
+ * be NULL (ids = 0..n-1).  Uploading invalidates the BVH. */
+int rt_set_spheres(rt_ctx* ctx, const float* h_center_radius, const float* h_material8,
+                   const int32_t* h_object_id, int64_t n);
+/* Triangle extension (BASELINE.json configs 2-4; the reference has spheres only).
+ * vertices: n x 9 (v0 v1 v2); material_id: n (may be NULL = 0); materials: m x 8. */
+int rt_set_triangles(rt_ctx* ctx, const float* h_vertices, const int32_t* h_material_id, int64_t n,
+                     const float* h_materials, int m);
+/* Scene::background_color (old/raytracer_core copy.h:226; interaction.py:297). */
+int rt_set_background(rt_ctx* ctx, const float rgb[3]);
+
+/* ---- BVH: replaces Scene::build_bvh / BVH::build (old/raytracer_core copy.cpp:104-110,
+ * old/bvh copy.cpp:111-199) and v2 SceneIntersector::build_bvh + BVHBuilder::build
+ * (raytracer_core.cpp:57-141,165-189).
+ * builder 0 = the reference's top-down median split (leaf <= 4, longest axis, median by box
+ *             centre), built on the host, deterministic;
+ * builder 1 = LBVH built on the device (Morton order), for interactive edits.
+ * rt_get_bvh / rt_set_bvh let a checker walk the very same tree (nodes may be NULL to query
+ * the count).  prim_index has n entries. */
+int rt_build_bvh(rt_ctx* ctx, int builder);
+int rt_get_bvh(rt_ctx* ctx, rt_bvh_node* h_nodes, int64_t* n_nodes, int32_t* h_prim_index);
+int rt_set_bvh(rt_ctx* ctx, const rt_bvh_node* h_nodes, int64_t n_nodes, const int32_t* h_prim_index);
+/* Context-free host build with builder 0 (no device needed): for offline BVH caching and for
+ * checking the builder on machines without a GPU.  h_prims = n x 4 spheres or n x 9 triangles.
+ * Returns the node count through *n_nodes (call with h_nodes == NULL to size the arrays:
+ * at most 2*n + 2 records). */
+int rt_build_bvh_host(const float* h_prims, int is_triangles, int64_t n, rt_bvh_node* h_nodes,
+                      int64_t* n_nodes, int32_t* h_prim_index);
+
+/* ---- camera: replaces RayTracer::set_camera (old/raytracer_core copy.h:266) + the basis that
+ * Camera::get_ray recomputes per ray (old/raytracer_core copy.h:160-184).  aspect <= 0 means
+ * "use W/H of each render call" (what RayTracer::render does, old/raytracer_core copy.cpp:259).
+ * rt_get_camera_block returns pos3 fwd3 right3 up3 sx sy as doubles. */
+int rt_set_camera(rt_ctx* ctx, const double pos[3], const double target[3], const double up[3],
+                  double fov_deg, double aspect);
+int rt_get_camera_block(rt_ctx* ctx, int width, int height, double out[14]);
+
+/* ---- primary-hit AOV: the parity hook.  Replaces the per-pixel use of Scene::hit
+ * (old/raytracer_core copy.cpp:112-131) / SceneIntersector::intersect (raytracer_core.cpp:191-273)
+ * for camera rays through pixel centres u=(i+.5)/W, v=(j+.5)/H, t in [0.001, 1e10].
+ * d_prim: W*H int32 primitive number in upload order (-1 = miss); d_t: W*H float (0 on miss). */
+int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float* d_t, void* stream);
+/* Arbitrary rays (origin, direction; normalised like the Ray ctor raytracer_core.h:113). */
+int rt_trace_rays(rt_ctx* ctx, const float* d_origin, const float* d_direction, int64_t n,
+                  int32_t* d_prim, float* d_t, void* stream);
+/* RayTracer::select_object (old/raytracer_core copy.cpp:245-248): closest object id under the
+ * normalised screen position (x,y), t in [0.001, 1000], or -1.  Synchronous. */
+int rt_select_object(rt_ctx* ctx, double x, double y, int width, int height, int32_t* out_object_id);
+
+/* ---- render: replaces RayTracer::render (old/raytracer_core copy.cpp:257-318) /
+ * PathTracer::render (raytracer_core.cpp:354-416): spp jittered camera samples per pixel,
+ * path tracing to max_depth, mean -> sqrt gamma -> clamp [0,1], RGB float32, row-major, top
+ * row first.  d_out: H*W*3 floats.  Samples use Philox4x32-10 keyed by `seed`, counter
+ * (pixel, sample_offset + s, bounce, draw): successive progressive batches pass successive
+ * sample_offset values (v1 keeps thread-local generator state across calls instead). */
+int rt_render(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed,
+              uint32_t sample_offset, float* d_out, void* stream);
+/* Same, for the interleaved tiles {first_tile + k*tile_stride} of the frame cut into
+ * tile_w x tile_h tiles (row-major tile numbering) -- the multi-GPU partition.  d_out is the
+ * compact buffer [k][tile_h][tile_w][3]; resolve = 0 writes raw radiance sums instead. */
+int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int first_tile,
+                    int tile_stride, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
+                    int resolve, float* d_out, void* stream);
+/* Scatter gathered compact tile buffers [rank][k][tile_h][tile_w][3] back into a H*W*3 frame. */
+int rt_untile(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int n_ranks,
+              const float* d_tiles, float* d_frame, void* stream);
+/* Host-buffer convenience used by the reference-facing plugin call: render into a context-owned
+ * device framebuffer and copy it to h_out (H*W*3 floats; pinned memory makes the copy async-fast).
+ * Synchronous: returns when h_out is complete. */
+int rt_render_host(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed,
+                   uint32_t sample_offset, float* h_out);
+
+/* ---- progressive accumulation: replaces the numpy running mean of gamma'd batches in
+ * interaction.py:1311-1325: accum = accum * n_old/(n_old+n_batch) + batch * n_batch/(n_old+n_batch)
+ * (n_old == 0: accum = batch). */
+int rt_accumulate(rt_ctx* ctx, const float* d_batch, float* d_accum, int64_t n_floats, int n_old,
+                  int n_batch, void* stream);
+/* Display chain of interaction.py:1435-1439 + gui.py:73: x*e/(1+x*e) -> clip -> *255 -> uint8. */
+int rt_tonemap_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_floats, float exposure,
+                  void* stream);
+
+/* ---- options and counters.  Options: "integrator" 0 = v1 semantics (default; the generation
+ * that runs: RR `depth<3 || rand<0.8` unweighted, metal chosen with probability metallic),
+ * 1 = v2 semantics (raytracer_core.cpp:317-347); "stats" 0/1; "kernel" traversal variant
+ * (0 = default); "wavefront" 0/1. */
+int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);
+int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value);
+int rt_get_stats(rt_ctx* ctx, rt_stats* out);   /* synchronises the device */
+int rt_reset_stats(rt_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RT_H */

@@ -1,0 +1,569 @@
+// rt_api.cu -- the C ABI of libb200rt.so (include/b200rt.h): context, scene upload, BVH
+// management, camera, and the launches of the render hot path.  No torch types, no CPU render
+// fallback: every tracing entry point runs the sm_100a kernels of rt_kernels.cu.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200rt.h"
+#include "rt_bvh.h"
+#include "rt_kernels.h"
+
+using namespace b200rt;
+
+struct rt_ctx {
+    int device = 0;
+    int sm_count = 148;
+    std::recursive_mutex mu;
+    std::string err;
+
+    // host copy of the scene (RayTracer::set_scene deep-copies, old/raytracer_core copy.cpp:162-167)
+    bool is_tri = false;
+    int64_t n = 0;
+    std::vector<float> prim_data;      // spheres: n x 4; triangles: n x 9 (as uploaded)
+    std::vector<float> mats;           // m x 8
+    std::vector<int32_t> mat_id;       // triangles only
+    std::vector<int32_t> object_id;
+    int m = 0;
+    float bg[3] = {0.1f, 0.1f, 0.1f};  // Scene::Scene(), old/raytracer_core copy.cpp:54
+
+    // host BVH
+    std::vector<rt_bvh_node> nodes;
+    std::vector<int32_t> prim_index;
+    bool bvh_valid = false;
+    int bvh_depth = 0;
+
+    // device copies
+    float4* d_nodes = nullptr;
+    float4* d_prims = nullptr;
+    int* d_slot_prim = nullptr;
+    float4* d_mats = nullptr;
+    bool device_valid = false;
+
+    // camera (Camera::Camera(), old/raytracer_core copy.h:158)
+    double pos[3] = {0, 2, 3}, target[3] = {0, 0, -3}, up[3] = {0, 1, 0};
+    double fov = 45.0, aspect = 1.333;
+
+    // options
+    int integrator = 0, stats = 0, kernel = 0, wavefront = 0;
+
+    unsigned int* d_work_counter = nullptr;
+    unsigned long long* d_stats = nullptr;   // rays, segments, node_records, prim_tests
+    uint64_t launches = 0;
+
+    float* d_fb = nullptr;                   // rt_render_host framebuffer
+    size_t fb_floats = 0;
+    int32_t* d_pick = nullptr;               // rt_select_object scratch: org3 dir3 | prim | t
+};
+
+namespace {
+
+std::string g_create_error;
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int fail(rt_ctx* c, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return 1;
+}
+int cuda_fail(rt_ctx* c, const char* what, cudaError_t e) {
+    return fail(c, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e_ = (call);                              \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, #call, e_); \
+    } while (0)
+
+void free_device_scene(rt_ctx* c) {
+    cudaFree(c->d_nodes); cudaFree(c->d_prims); cudaFree(c->d_slot_prim); cudaFree(c->d_mats);
+    c->d_nodes = c->d_prims = c->d_mats = nullptr; c->d_slot_prim = nullptr;
+    c->device_valid = false;
+}
+
+// Camera basis exactly as Camera::get_ray builds it (old/raytracer_core copy.h:160-184): forward
+// from target, right = forward x world-up (0,1,0) with the (1,0,0) fallback, up = right x forward,
+// tan(fov * 3.14159 / 360).  Like the reference, Camera::up is carried but not read.
+CameraBlock camera_block(const rt_ctx* c, double aspect) {
+    auto norm = [](double* v) {
+        double l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (l > 0) { v[0] /= l; v[1] /= l; v[2] /= l; }
+    };
+    double f[3] = {c->target[0] - c->pos[0], c->target[1] - c->pos[1], c->target[2] - c->pos[2]};
+    norm(f);
+    double r[3] = {f[1] * 0.0 - f[2] * 1.0, f[2] * 0.0 - f[0] * 0.0, f[0] * 1.0 - f[1] * 0.0};
+    norm(r);
+    if (std::sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) < 0.001) { r[0] = 1; r[1] = 0; r[2] = 0; }
+    double u[3] = {r[1] * f[2] - r[2] * f[1], r[2] * f[0] - r[0] * f[2], r[0] * f[1] - r[1] * f[0]};
+    norm(u);
+    double tan_fov = std::tan(c->fov * 3.14159 / 360.0);
+    CameraBlock b;
+    b.px = (float)c->pos[0]; b.py = (float)c->pos[1]; b.pz = (float)c->pos[2]; b.pad_ = 0.0f;
+    for (int k = 0; k < 3; ++k) { b.fwd[k] = f[k]; b.right[k] = r[k]; b.up[k] = u[k]; }
+    b.sx = aspect * tan_fov;
+    b.sy = tan_fov;
+    return b;
+}
+
+int ensure_bvh(rt_ctx* ctx);
+
+// Host scene + BVH -> device arrays in leaf order.
+int ensure_device(rt_ctx* ctx) {
+    if (ctx->device_valid) return 0;
+    if (int rc = ensure_bvh(ctx)) return rc;
+    free_device_scene(ctx);
+    const int64_t n = ctx->n;
+    const int64_t n_nodes = (int64_t)ctx->nodes.size();
+    if (n > 0) {
+        const int per = ctx->is_tri ? 3 : 1;
+        std::vector<float4> prims((size_t)n * per);
+        for (int64_t slot = 0; slot < n; ++slot) {
+            const int32_t p = ctx->prim_index[slot];
+            if (ctx->is_tri) {
+                const float* v = &ctx->prim_data[9 * (size_t)p];
+                int32_t mid = ctx->mat_id[p];
+                float pw, mw;
+                std::memcpy(&pw, &p, 4); std::memcpy(&mw, &mid, 4);
+                prims[3 * slot + 0] = make_float4(v[0], v[1], v[2], pw);
+                prims[3 * slot + 1] = make_float4(v[3] - v[0], v[4] - v[1], v[5] - v[2], mw);   // e1 = v1 - v0
+                prims[3 * slot + 2] = make_float4(v[6] - v[0], v[7] - v[1], v[8] - v[2], 0.0f); // e2 = v2 - v0
+            } else {
+                const float* s = &ctx->prim_data[4 * (size_t)p];
+                prims[slot] = make_float4(s[0], s[1], s[2], s[3]);
+            }
+        }
+        CK(cudaMalloc(&ctx->d_prims, prims.size() * sizeof(float4)));
+        CK(cudaMemcpy(ctx->d_prims, prims.data(), prims.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->d_slot_prim, (size_t)n * sizeof(int)));
+        CK(cudaMemcpy(ctx->d_slot_prim, ctx->prim_index.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->d_nodes, (size_t)n_nodes * sizeof(rt_bvh_node)));
+        CK(cudaMemcpy(ctx->d_nodes, ctx->nodes.data(), (size_t)n_nodes * sizeof(rt_bvh_node), cudaMemcpyHostToDevice));
+    }
+    const int m = ctx->m;
+    if (m > 0) {
+        std::vector<float4> mats((size_t)m * 2);
+        for (int k = 0; k < m; ++k) {
+            const float* s = &ctx->mats[8 * (size_t)k];
+            mats[2 * k + 0] = make_float4(s[0], s[1], s[2], s[3]);   // albedo | metallic
+            mats[2 * k + 1] = make_float4(s[4], s[5], s[6], s[7]);   // roughness | emission
+        }
+        CK(cudaMalloc(&ctx->d_mats, mats.size() * sizeof(float4)));
+        CK(cudaMemcpy(ctx->d_mats, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    ctx->device_valid = true;
+    return 0;
+}
+
+int ensure_bvh(rt_ctx* ctx) {
+    if (ctx->bvh_valid) return 0;
+    return rt_build_bvh(ctx, 0);
+}
+
+SceneView scene_view(const rt_ctx* c) {
+    SceneView v;
+    v.nodes = c->d_nodes; v.prims = c->d_prims; v.slot_prim = c->d_slot_prim; v.mats = c->d_mats;
+    v.n_prims = (int)c->n; v.n_nodes = (int)c->nodes.size();
+    v.bg_r = c->bg[0]; v.bg_g = c->bg[1]; v.bg_b = c->bg[2];
+    return v;
+}
+
+LaunchCfg launch_cfg(rt_ctx* c, void* stream) {
+    LaunchCfg cfg;
+    cfg.stream = (cudaStream_t)stream;
+    cfg.sm_count = c->sm_count;
+    cfg.d_work_counter = c->d_work_counter;
+    cfg.d_stats = c->stats ? c->d_stats : nullptr;
+    return cfg;
+}
+
+TileMap full_frame_map(int width, int height) {
+    TileMap tm;
+    tm.width = width; tm.height = height;
+    tm.tile_w = 32; tm.tile_h = 32;                       // TILE_SIZE, old/raytracer_core copy.cpp:264
+    tm.tiles_x = (width + 31) / 32;
+    tm.n_tiles = tm.tiles_x * ((height + 31) / 32);
+    tm.first_tile = 0; tm.tile_stride = 1; tm.n_local_tiles = tm.n_tiles;
+    tm.compact = 0;
+    return tm;
+}
+
+int check_frame(rt_ctx* ctx, int width, int height) {
+    if (width <= 0 || height <= 0 || (int64_t)width * height > (int64_t)1 << 30) return fail(ctx, "invalid frame size");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rt_abi_version(void) { return B200RT_ABI_VERSION; }
+
+int rt_create(int device, rt_ctx** out) {
+    if (!out) return fail(nullptr, "rt_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, std::string("rt_create: no CUDA device (") + cudaGetErrorString(e) +
+                                 "); libb200rt has no CPU fallback");
+    if (device < 0 || device >= count) return fail(nullptr, "rt_create: device index out of range");
+    rt_ctx* ctx = new rt_ctx();
+    ctx->device = device;
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return cuda_fail(nullptr, "cudaGetDeviceProperties", e); }
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(nullptr, "rt_create: device is not Blackwell (sm_100a) -- this library ships sm_100a code only");
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaMalloc(&ctx->d_work_counter, 64)) != cudaSuccess || (e = cudaMalloc(&ctx->d_stats, 64)) != cudaSuccess ||
+        (e = cudaMemset(ctx->d_stats, 0, 64)) != cudaSuccess || (e = cudaMalloc(&ctx->d_pick, 64)) != cudaSuccess) {
+        delete ctx;
+        return cuda_fail(nullptr, "rt_create: cudaMalloc", e);
+    }
+    *out = ctx;
+    return 0;
+}
+
+void rt_destroy(rt_ctx* ctx) {
+    if (!ctx) return;
+    {
+        std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+        DeviceGuard g(ctx->device);
+        cudaDeviceSynchronize();
+        free_device_scene(ctx);
+        cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick);
+    }
+    delete ctx;
+}
+
+const char* rt_last_error(rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rt_set_spheres(rt_ctx* ctx, const float* cr, const float* mat8, const int32_t* object_id, int64_t n) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || n > (int64_t)1 << 28) return fail(ctx, "rt_set_spheres: invalid count");
+    if (n > 0 && (!cr || !mat8)) return fail(ctx, "rt_set_spheres: NULL array");
+    ctx->is_tri = false; ctx->n = n; ctx->m = (int)n;
+    ctx->prim_data.assign(cr, cr + 4 * n);
+    ctx->mats.assign(mat8, mat8 + 8 * n);
+    ctx->mat_id.clear();
+    ctx->object_id.resize(n);
+    for (int64_t i = 0; i < n; ++i) ctx->object_id[i] = object_id ? object_id[i] : (int32_t)i;
+    ctx->bvh_valid = false; ctx->device_valid = false;
+    return 0;
+}
+
+int rt_set_triangles(rt_ctx* ctx, const float* v, const int32_t* material_id, int64_t n, const float* materials, int m) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || n > (int64_t)1 << 28 || m < 0) return fail(ctx, "rt_set_triangles: invalid count");
+    if (n > 0 && (!v || !materials || m == 0)) return fail(ctx, "rt_set_triangles: NULL array / no material");
+    ctx->is_tri = true; ctx->n = n; ctx->m = m;
+    ctx->prim_data.assign(v, v + 9 * n);
+    ctx->mats.assign(materials, materials + 8 * (size_t)m);
+    ctx->mat_id.resize(n);
+    ctx->object_id.resize(n);
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t id = material_id ? material_id[i] : 0;
+        if (id < 0 || id >= m) return fail(ctx, "rt_set_triangles: material_id out of range");
+        ctx->mat_id[i] = id;
+        ctx->object_id[i] = (int32_t)i;
+    }
+    ctx->bvh_valid = false; ctx->device_valid = false;
+    return 0;
+}
+
+int rt_set_background(rt_ctx* ctx, const float rgb[3]) {
+    if (!ctx || !rgb) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    std::memcpy(ctx->bg, rgb, 12);
+    return 0;
+}
+
+int rt_build_bvh(rt_ctx* ctx, int builder) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (builder != 0) return fail(ctx, "rt_build_bvh: builder 1 (device LBVH) is not available in this build");
+    PrimBoxes boxes;
+    if (ctx->is_tri) triangle_boxes(ctx->prim_data.data(), ctx->n, boxes);
+    else sphere_boxes(ctx->prim_data.data(), ctx->n, boxes);
+    build_median_split(boxes, ctx->n, ctx->nodes, ctx->prim_index);
+    const char* msg;
+    ctx->bvh_depth = validate_bvh(ctx->nodes.data(), (int64_t)ctx->nodes.size(), ctx->n, &msg);
+    if (ctx->bvh_depth < 0) return fail(ctx, msg);
+    if (ctx->bvh_depth > kStackDepth - 2) return fail(ctx, "rt_build_bvh: tree deeper than the traversal stack");
+    ctx->bvh_valid = true; ctx->device_valid = false;
+    return 0;
+}
+
+int rt_build_bvh_host(const float* h_prims, int is_triangles, int64_t n, rt_bvh_node* h_nodes, int64_t* n_nodes,
+                      int32_t* h_prim_index) {
+    if (n < 0 || (n > 0 && !h_prims) || !n_nodes) return fail(nullptr, "rt_build_bvh_host: bad arguments");
+    PrimBoxes boxes;
+    if (is_triangles) triangle_boxes(h_prims, n, boxes); else sphere_boxes(h_prims, n, boxes);
+    std::vector<rt_bvh_node> nodes;
+    std::vector<int32_t> prim_index;
+    build_median_split(boxes, n, nodes, prim_index);
+    *n_nodes = (int64_t)nodes.size();
+    if (h_nodes && !nodes.empty()) std::memcpy(h_nodes, nodes.data(), nodes.size() * sizeof(rt_bvh_node));
+    if (h_prim_index && n) std::memcpy(h_prim_index, prim_index.data(), (size_t)n * sizeof(int32_t));
+    return 0;
+}
+
+int rt_get_bvh(rt_ctx* ctx, rt_bvh_node* nodes, int64_t* n_nodes, int32_t* prim_index) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (int rc = ensure_bvh(ctx)) return rc;
+    if (n_nodes) *n_nodes = (int64_t)ctx->nodes.size();
+    if (nodes && !ctx->nodes.empty()) std::memcpy(nodes, ctx->nodes.data(), ctx->nodes.size() * sizeof(rt_bvh_node));
+    if (prim_index && ctx->n) std::memcpy(prim_index, ctx->prim_index.data(), (size_t)ctx->n * sizeof(int32_t));
+    return 0;
+}
+
+int rt_set_bvh(rt_ctx* ctx, const rt_bvh_node* nodes, int64_t n_nodes, const int32_t* prim_index) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n_nodes < 0 || (n_nodes > 0 && (!nodes || !prim_index))) return fail(ctx, "rt_set_bvh: NULL array");
+    if (ctx->n > 0 && n_nodes == 0) return fail(ctx, "rt_set_bvh: empty tree for a non-empty scene");
+    const char* msg;
+    int depth = validate_bvh(nodes, n_nodes, ctx->n, &msg);
+    if (depth < 0) return fail(ctx, msg);
+    if (depth > kStackDepth - 2) return fail(ctx, "rt_set_bvh: tree deeper than the traversal stack");
+    std::vector<char> seen((size_t)ctx->n, 0);
+    for (int64_t k = 0; k < ctx->n; ++k) {
+        int32_t p = prim_index[k];
+        if (p < 0 || p >= ctx->n || seen[p]) return fail(ctx, "rt_set_bvh: prim_index is not a permutation");
+        seen[p] = 1;
+    }
+    ctx->nodes.assign(nodes, nodes + n_nodes);
+    ctx->prim_index.assign(prim_index, prim_index + ctx->n);
+    ctx->bvh_depth = depth;
+    ctx->bvh_valid = true; ctx->device_valid = false;
+    return 0;
+}
+
+int rt_set_camera(rt_ctx* ctx, const double pos[3], const double target[3], const double up[3], double fov_deg, double aspect) {
+    if (!ctx || !pos || !target) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    for (int k = 0; k < 3; ++k) { ctx->pos[k] = pos[k]; ctx->target[k] = target[k]; if (up) ctx->up[k] = up[k]; }
+    ctx->fov = fov_deg;
+    ctx->aspect = aspect;
+    return 0;
+}
+
+int rt_get_camera_block(rt_ctx* ctx, int width, int height, double out[14]) {
+    if (!ctx || !out) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    double aspect = (width > 0 && height > 0) ? (double)width / height : ctx->aspect;
+    CameraBlock b = camera_block(ctx, aspect);
+    out[0] = b.px; out[1] = b.py; out[2] = b.pz;
+    for (int k = 0; k < 3; ++k) { out[3 + k] = b.fwd[k]; out[6 + k] = b.right[k]; out[9 + k] = b.up[k]; }
+    out[12] = b.sx; out[13] = b.sy;
+    return 0;
+}
+
+int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float* d_t, void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (int rc = check_frame(ctx, width, height)) return rc;
+    if (!d_prim || !d_t) return fail(ctx, "rt_trace_primary: NULL output");
+    DeviceGuard g(ctx->device);
+    if (int rc = ensure_device(ctx)) return rc;
+    ctx->aspect = (double)width / height;            // RayTracer::render, old/raytracer_core copy.cpp:259
+    CameraBlock cam = camera_block(ctx, ctx->aspect);
+    CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, full_frame_map(width, height), d_prim, d_t,
+                            launch_cfg(ctx, stream)));
+    ctx->launches += 1;
+    return 0;
+}
+
+int rt_trace_rays(rt_ctx* ctx, const float* d_origin, const float* d_direction, int64_t n, int32_t* d_prim, float* d_t,
+                  void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || (n > 0 && (!d_origin || !d_direction || !d_prim || !d_t))) return fail(ctx, "rt_trace_rays: bad arguments");
+    DeviceGuard g(ctx->device);
+    if (int rc = ensure_device(ctx)) return rc;
+    CK(launch_trace_rays(scene_view(ctx), ctx->is_tri, d_origin, d_direction, n, d_prim, d_t, launch_cfg(ctx, stream)));
+    if (n) ctx->launches += 1;
+    return 0;
+}
+
+int rt_select_object(rt_ctx* ctx, double x, double y, int width, int height, int32_t* out_object_id) {
+    if (!ctx || !out_object_id) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    if (int rc = ensure_device(ctx)) return rc;
+    (void)width; (void)height;                       // the reference ignores them too (camera.aspect_ratio is used)
+    CameraBlock b = camera_block(ctx, ctx->aspect);
+    double vx = (x - 0.5) * 2.0 * b.sx, vy = (0.5 - y) * 2.0 * b.sy;
+    float host[8];
+    host[0] = b.px; host[1] = b.py; host[2] = b.pz;
+    double d[3];
+    for (int k = 0; k < 3; ++k) d[k] = b.fwd[k] + b.right[k] * vx + b.up[k] * vy;
+    double l = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    for (int k = 0; k < 3; ++k) host[3 + k] = (float)(d[k] / l);
+    float* dv = reinterpret_cast<float*>(ctx->d_pick);
+    CK(cudaMemcpy(dv, host, 24, cudaMemcpyHostToDevice));
+    LaunchCfg cfg = launch_cfg(ctx, nullptr);
+    cfg.d_stats = nullptr;
+    CK(launch_trace_rays(scene_view(ctx), ctx->is_tri, dv, dv + 3, 1, ctx->d_pick + 6, dv + 7, cfg));
+    ctx->launches += 1;
+    int32_t prim; float t;
+    CK(cudaMemcpy(&prim, ctx->d_pick + 6, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&t, dv + 7, 4, cudaMemcpyDeviceToHost));
+    // cast_ray_for_selection(ray, 0.001, 1000.0), old/raytracer_core copy.cpp:247
+    *out_object_id = (prim >= 0 && t <= 1000.0f) ? ctx->object_id[prim] : -1;
+    return 0;
+}
+
+int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int first_tile, int tile_stride, int spp,
+                    int max_depth, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out, void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (int rc = check_frame(ctx, width, height)) return rc;
+    if (tile_w <= 0 || tile_h <= 0 || (tile_w & 7) || (tile_h & 3)) return fail(ctx, "rt_render_tiles: tile must be a multiple of 8x4");
+    if (first_tile < 0 || tile_stride <= 0 || spp <= 0 || max_depth < 0 || !d_out) return fail(ctx, "rt_render_tiles: bad arguments");
+    DeviceGuard g(ctx->device);
+    if (int rc = ensure_device(ctx)) return rc;
+    ctx->aspect = (double)width / height;
+    CameraBlock cam = camera_block(ctx, ctx->aspect);
+    TileMap tm;
+    tm.width = width; tm.height = height; tm.tile_w = tile_w; tm.tile_h = tile_h;
+    tm.tiles_x = (width + tile_w - 1) / tile_w;
+    tm.n_tiles = tm.tiles_x * ((height + tile_h - 1) / tile_h);
+    tm.first_tile = first_tile; tm.tile_stride = tile_stride;
+    tm.n_local_tiles = first_tile < tm.n_tiles ? (tm.n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
+    tm.compact = 1;
+    CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
+                     d_out, launch_cfg(ctx, stream)));
+    if (tm.n_local_tiles) ctx->launches += 1;
+    return 0;
+}
+
+int rt_render(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
+              float* d_out, void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (int rc = check_frame(ctx, width, height)) return rc;
+    if (spp <= 0 || max_depth < 0 || !d_out) return fail(ctx, "rt_render: bad arguments");
+    DeviceGuard g(ctx->device);
+    if (int rc = ensure_device(ctx)) return rc;
+    ctx->aspect = (double)width / height;
+    CameraBlock cam = camera_block(ctx, ctx->aspect);
+    CK(launch_render(scene_view(ctx), ctx->is_tri, cam, full_frame_map(width, height), spp, max_depth, ctx->integrator,
+                     seed, sample_offset, 1, d_out, launch_cfg(ctx, stream)));
+    ctx->launches += 1;
+    return 0;
+}
+
+int rt_untile(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int n_ranks, const float* d_tiles, float* d_frame,
+              void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (int rc = check_frame(ctx, width, height)) return rc;
+    if (tile_w <= 0 || tile_h <= 0 || n_ranks <= 0 || !d_tiles || !d_frame) return fail(ctx, "rt_untile: bad arguments");
+    DeviceGuard g(ctx->device);
+    CK(launch_untile(width, height, tile_w, tile_h, n_ranks, d_tiles, d_frame, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int rt_render_host(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
+                   float* h_out) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (int rc = check_frame(ctx, width, height)) return rc;
+    if (!h_out) return fail(ctx, "rt_render_host: NULL output");
+    DeviceGuard g(ctx->device);
+    size_t need = (size_t)width * height * 3;
+    if (need > ctx->fb_floats) {
+        cudaFree(ctx->d_fb); ctx->d_fb = nullptr; ctx->fb_floats = 0;
+        CK(cudaMalloc(&ctx->d_fb, need * sizeof(float)));
+        ctx->fb_floats = need;
+    }
+    if (int rc = rt_render(ctx, width, height, spp, max_depth, seed, sample_offset, ctx->d_fb, nullptr)) return rc;
+    CK(cudaMemcpy(h_out, ctx->d_fb, need * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int rt_accumulate(rt_ctx* ctx, const float* d_batch, float* d_accum, int64_t n, int n_old, int n_batch, void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || n_old < 0 || n_batch <= 0 || (n > 0 && (!d_batch || !d_accum))) return fail(ctx, "rt_accumulate: bad arguments");
+    DeviceGuard g(ctx->device);
+    CK(launch_accumulate(d_batch, d_accum, n, n_old, n_batch, (cudaStream_t)stream));
+    if (n) ctx->launches += 1;
+    return 0;
+}
+
+int rt_tonemap_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n, float exposure, void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || (n > 0 && (!d_accum || !d_rgb8))) return fail(ctx, "rt_tonemap_u8: bad arguments");
+    DeviceGuard g(ctx->device);
+    CK(launch_tonemap_u8(d_accum, d_rgb8, n, exposure, (cudaStream_t)stream));
+    if (n) ctx->launches += 1;
+    return 0;
+}
+
+int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    std::string k(name);
+    if (k == "integrator") { if (value != 0 && value != 1) return fail(ctx, "integrator must be 0 (v1) or 1 (v2)"); ctx->integrator = (int)value; }
+    else if (k == "stats") ctx->stats = value != 0;
+    else if (k == "kernel") ctx->kernel = (int)value;
+    else if (k == "wavefront") ctx->wavefront = value != 0;
+    else return fail(ctx, "rt_set_option: unknown option '" + k + "'");
+    return 0;
+}
+
+int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
+    if (!ctx || !name || !value) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    std::string k(name);
+    if (k == "integrator") *value = ctx->integrator;
+    else if (k == "stats") *value = ctx->stats;
+    else if (k == "kernel") *value = ctx->kernel;
+    else if (k == "wavefront") *value = ctx->wavefront;
+    else if (k == "sm_count") *value = ctx->sm_count;
+    else if (k == "bvh_depth") *value = ctx->bvh_depth;
+    else if (k == "n_prims") *value = ctx->n;
+    else if (k == "n_nodes") *value = (int64_t)ctx->nodes.size();
+    else return fail(ctx, "rt_get_option: unknown option '" + k + "'");
+    return 0;
+}
+
+int rt_get_stats(rt_ctx* ctx, rt_stats* out) {
+    if (!ctx || !out) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    unsigned long long v[4];
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(v, ctx->d_stats, sizeof(v), cudaMemcpyDeviceToHost));
+    out->rays = v[0]; out->segments = v[1]; out->node_records = v[2]; out->prim_tests = v[3];
+    out->launches = ctx->launches;
+    return 0;
+}
+
+int rt_reset_stats(rt_ctx* ctx) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaMemset(ctx->d_stats, 0, 64));
+    ctx->launches = 0;
+    return 0;
+}
+
+}  // extern "C"

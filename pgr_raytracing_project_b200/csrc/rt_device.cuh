@@ -1,0 +1,328 @@
+// rt_device.cuh -- device-side building blocks of the render hot path (sm_100a).
+//
+// Arithmetic contract: IEEE float32/float64, this translation unit is compiled
+// with -fmad=false so nothing is contracted implicitly; every fused multiply-add below is an
+// explicit __fmaf_rn.  sqrt and division are the IEEE-rounded ones (nvcc defaults
+// -prec-sqrt=true -prec-div=true; never build this with --use_fast_math).  The CPU checker in
+// oracle/ follows the same contract, written independently, which is what makes hit ids, hit
+// distances and whole images comparable bit for bit.
+//
+// Reference lines restated here (all under /root/reference):
+//   camera ray ............ old/raytracer_core copy.h:160-184, old/raytracer_core copy.cpp:288-289
+//   ray setup ............. cpp_raytracer/raytracer_core.h:107-121
+//   slab test ............. cpp_raytracer/raytracer_core.h:132-153 + swap of old/bvh copy.cpp:15-17
+//   sphere test ........... old/raytracer_core copy.cpp:21-52
+//   traversal ............. cpp_raytracer/raytracer_core.cpp:198-243 (closest hit, shrinking tmax)
+//   integrators ........... old/raytracer_core copy.cpp:211-243 (0), raytracer_core.cpp:291-351 (1)
+//   resolve ............... cpp_raytracer/raytracer_core.cpp:398-409
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200rt {
+
+constexpr float kTMin = 0.001f;   // old/raytracer_core copy.cpp:217
+constexpr float kTMax = 1e10f;
+constexpr int kStackDepth = 64;   // cpp_raytracer/raytracer_core.cpp:200
+
+struct CameraBlock {              // basis in double: primary directions are rounded to f32 once
+    float px, py, pz;
+    float pad_;
+    double fwd[3], right[3], up[3];
+    double sx, sy;                // aspect * tan(fov/2), tan(fov/2)
+};
+
+struct SceneView {
+    const float4* __restrict__ nodes;      // 2 x float4 per 32-byte node (rt_bvh_node)
+    const float4* __restrict__ prims;      // leaf order; triangle: v0|prim, e1|material, e2|0 ; sphere: c|r
+    const int* __restrict__ slot_prim;     // slot -> primitive number (upload order)
+    const float4* __restrict__ mats;       // 2 x float4 per material: albedo|metallic, roughness|emission
+    int n_prims;
+    int n_nodes;
+    float bg_r, bg_g, bg_b;
+};
+
+struct Counters { unsigned long long nodes, prims, segments; };
+
+struct Ray { float ox, oy, oz, dx, dy, dz, ix, iy, iz, ax, ay, az; };   // a = o * inv (slab offsets)
+
+// ------------------------------------------------------------------------------- math
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fmaf_rn(az, bz, __fmaf_rn(ay, by, __fmul_rn(ax, bx)));
+}
+__device__ __forceinline__ void cross3(float ax, float ay, float az, float bx, float by, float bz,
+                                       float& rx, float& ry, float& rz) {
+    rx = __fmaf_rn(ay, bz, -__fmul_rn(az, by));
+    ry = __fmaf_rn(az, bx, -__fmul_rn(ax, bz));
+    rz = __fmaf_rn(ax, by, -__fmul_rn(ay, bx));
+}
+__device__ __forceinline__ void normalize3(float& x, float& y, float& z) {   // raytracer_core.h:91-94
+    float len = __fsqrt_rn(dot3(x, y, z, x, y, z));
+    if (len > 0.0f) {
+        float inv = __fdiv_rn(1.0f, len);
+        x = __fmul_rn(x, inv); y = __fmul_rn(y, inv); z = __fmul_rn(z, inv);
+    } else { x = 0.0f; y = 0.0f; z = 1.0f; }
+}
+
+// ------------------------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float u01(uint32_t x) { return __fmul_rn((float)(x >> 8), 0x1p-24f); }
+
+// ------------------------------------------------------------------------------- rays
+__device__ __forceinline__ Ray make_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
+    Ray r;
+    r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+    r.ix = __fdiv_rn(1.0f, dx); r.iy = __fdiv_rn(1.0f, dy); r.iz = __fdiv_rn(1.0f, dz);
+    r.ax = __fmul_rn(ox, r.ix); r.ay = __fmul_rn(oy, r.iy); r.az = __fmul_rn(oz, r.iz);
+    return r;
+}
+
+// Camera ray through pixel (i + jx, j + jy); direction evaluated in double, rounded once.
+__device__ __forceinline__ Ray camera_ray(const CameraBlock& c, int i, int j, float jx, float jy,
+                                          double inv_w, double inv_h) {
+    double u = __dmul_rn(__dadd_rn((double)i, (double)jx), inv_w);
+    double v = __dmul_rn(__dadd_rn((double)j, (double)jy), inv_h);
+    double ndc_x = __dmul_rn(__dsub_rn(u, 0.5), 2.0);
+    double ndc_y = __dmul_rn(__dsub_rn(0.5, v), 2.0);
+    double vx = __dmul_rn(ndc_x, c.sx), vy = __dmul_rn(ndc_y, c.sy);
+    double dx = __dadd_rn(__dadd_rn(c.fwd[0], __dmul_rn(c.right[0], vx)), __dmul_rn(c.up[0], vy));
+    double dy = __dadd_rn(__dadd_rn(c.fwd[1], __dmul_rn(c.right[1], vx)), __dmul_rn(c.up[1], vy));
+    double dz = __dadd_rn(__dadd_rn(c.fwd[2], __dmul_rn(c.right[2], vx)), __dmul_rn(c.up[2], vy));
+    double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+    double il = __ddiv_rn(1.0, len);
+    return make_ray(c.px, c.py, c.pz, (float)__dmul_rn(dx, il), (float)__dmul_rn(dy, il), (float)__dmul_rn(dz, il));
+}
+
+// ------------------------------------------------------------------------------- intersection
+struct Hit { float t; int prim; int slot; };
+
+__device__ __forceinline__ bool box_hit(const float4& lo, const float4& hi, const Ray& r, float tlo,
+                                        float thi, float& tn) {
+    float x1 = __fmaf_rn(lo.x, r.ix, -r.ax), x2 = __fmaf_rn(hi.x, r.ix, -r.ax);
+    float y1 = __fmaf_rn(lo.y, r.iy, -r.ay), y2 = __fmaf_rn(hi.y, r.iy, -r.ay);
+    float z1 = __fmaf_rn(lo.z, r.iz, -r.az), z2 = __fmaf_rn(hi.z, r.iz, -r.az);
+    float n = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fmaxf(fminf(z1, z2), tlo));
+    float f = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), thi));
+    tn = n;
+    return n <= f;
+}
+
+// closest-hit update; ties go to the lower primitive number
+__device__ __forceinline__ void consider(Hit& h, float t, int prim, int slot) {
+    if (!(t >= kTMin && t <= h.t)) return;
+    if (t < h.t || h.prim < 0 || prim < h.prim) { h.t = t; h.prim = prim; h.slot = slot; }
+}
+
+template <bool TRI>
+__device__ __forceinline__ void test_prim(const SceneView& sc, int slot, const Ray& r, Hit& h) {
+    if (TRI) {
+        const float4* p = sc.prims + 3 * (size_t)slot;
+        float4 v0 = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
+        float px, py, pz;
+        cross3(r.dx, r.dy, r.dz, e2.x, e2.y, e2.z, px, py, pz);
+        float det = dot3(e1.x, e1.y, e1.z, px, py, pz);
+        if (det == 0.0f) return;
+        float inv = __fdiv_rn(1.0f, det);
+        float sx = __fsub_rn(r.ox, v0.x), sy = __fsub_rn(r.oy, v0.y), sz = __fsub_rn(r.oz, v0.z);
+        float u = __fmul_rn(dot3(sx, sy, sz, px, py, pz), inv);
+        if (!(u >= 0.0f && u <= 1.0f)) return;
+        float qx, qy, qz;
+        cross3(sx, sy, sz, e1.x, e1.y, e1.z, qx, qy, qz);
+        float v = __fmul_rn(dot3(r.dx, r.dy, r.dz, qx, qy, qz), inv);
+        if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return;
+        float t = __fmul_rn(dot3(e2.x, e2.y, e2.z, qx, qy, qz), inv);
+        consider(h, t, __float_as_int(v0.w), slot);
+    } else {
+        // v1 Sphere::hit in double on the float32 ray / sphere, roots rounded to float32
+        float4 s = __ldg(sc.prims + slot);
+        double ocx = __dsub_rn((double)r.ox, (double)s.x), ocy = __dsub_rn((double)r.oy, (double)s.y),
+               ocz = __dsub_rn((double)r.oz, (double)s.z);
+        double dx = r.dx, dy = r.dy, dz = r.dz, rad = s.w;
+        double a = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        double half_b = __dadd_rn(__dadd_rn(__dmul_rn(ocx, dx), __dmul_rn(ocy, dy)), __dmul_rn(ocz, dz));
+        double c = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(ocx, ocx), __dmul_rn(ocy, ocy)), __dmul_rn(ocz, ocz)),
+                             __dmul_rn(rad, rad));
+        double disc = __dsub_rn(__dmul_rn(half_b, half_b), __dmul_rn(a, c));
+        if (disc < 0.0) return;
+        double sq = __dsqrt_rn(disc);
+        float t = (float)__ddiv_rn(__dsub_rn(-half_b, sq), a);
+        if (!(t >= kTMin && t <= h.t)) t = (float)__ddiv_rn(__dadd_rn(-half_b, sq), a);
+        if (!(t >= kTMin && t <= h.t)) return;
+        consider(h, t, __ldg(sc.slot_prim + slot), slot);
+    }
+}
+
+// Closest hit over the flattened BVH: sibling pairs fetched as 4 x LDG.128 (ld.global.nc.v4),
+// nearer child first, farther child pushed with its entry distance, dropped on pop when that
+// distance exceeds the closest hit.  (Same visiting order as oracle MODE_NEAR_FIRST, so the
+// node / primitive counters agree exactly with the CPU checker.)
+template <bool TRI, bool STATS>
+__device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit& h, Counters& cnt) {
+    h.t = kTMax; h.prim = -1; h.slot = -1;
+    if (sc.n_nodes == 0) return;
+    float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
+    float tn;
+    if (STATS) cnt.nodes += 1;
+    if (!box_hit(lo, hi, r, kTMin, h.t, tn)) return;
+    int ca = __float_as_int(lo.w), cb = __float_as_int(hi.w);
+    int stack_code[kStackDepth];
+    float stack_tn[kStackDepth];
+    int sp = 0;
+    for (;;) {
+        if (cb == 0) {
+            const float4* p = sc.nodes + 2 * (size_t)ca;
+            float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
+            if (STATS) cnt.nodes += 2;
+            float tl, tr;
+            bool hl = box_hit(l0, l1, r, kTMin, h.t, tl);
+            bool hr = box_hit(r0, r1, r, kTMin, h.t, tr);
+            int la = __float_as_int(l0.w), lb = __float_as_int(l1.w);
+            int ra = __float_as_int(r0.w), rb = __float_as_int(r1.w);
+            if (hl && hr) {
+                if (tr < tl) { int t0 = la; la = ra; ra = t0; t0 = lb; lb = rb; rb = t0; float tf = tl; tl = tr; tr = tf; }
+                stack_code[sp] = rb == 0 ? ra : ~((ra << 3) | rb);
+                stack_tn[sp] = tr;
+                ++sp;
+                ca = la; cb = lb;
+                continue;
+            } else if (hl) { ca = la; cb = lb; continue; }
+            else if (hr) { ca = ra; cb = rb; continue; }
+        } else {
+            for (int k = 0; k < cb; ++k) {
+                if (STATS) cnt.prims += 1;
+                test_prim<TRI>(sc, ca + k, r, h);
+            }
+        }
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            if (stack_tn[sp] <= h.t) {
+                int code = stack_code[sp];
+                if (code >= 0) { ca = code; cb = 0; } else { code = ~code; ca = code >> 3; cb = code & 7; }
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+    }
+}
+
+// ------------------------------------------------------------------------------- shading
+template <bool TRI>
+__device__ __forceinline__ void shading_normal(const SceneView& sc, const Hit& h, const Ray& r, float px,
+                                               float py, float pz, float& nx, float& ny, float& nz) {
+    if (TRI) {
+        const float4* p = sc.prims + 3 * (size_t)h.slot;
+        float4 e1 = __ldg(p + 1), e2 = __ldg(p + 2);
+        cross3(e1.x, e1.y, e1.z, e2.x, e2.y, e2.z, nx, ny, nz);
+        normalize3(nx, ny, nz);
+    } else {
+        float4 s = __ldg(sc.prims + h.slot);
+        float inv = __fdiv_rn(1.0f, s.w);                           // raytracer_core.h:210
+        nx = __fmul_rn(__fsub_rn(px, s.x), inv); ny = __fmul_rn(__fsub_rn(py, s.y), inv); nz = __fmul_rn(__fsub_rn(pz, s.z), inv);
+    }
+    if (!(dot3(r.dx, r.dy, r.dz, nx, ny, nz) < 0.0f)) { nx = -nx; ny = -ny; nz = -nz; }   // old/..core copy.h:132-135
+}
+
+__device__ __forceinline__ void unit_sphere(uint32_t pixel, uint32_t sample, uint32_t bounce, uint32_t k0,
+                                            uint32_t k1, float& x, float& y, float& z) {
+    for (uint32_t j = 0;; ++j) {                                      // old/raytracer_core copy.cpp:170-178
+        uint4 o = philox4x32_10(pixel, sample, bounce, 1u + j, k0, k1);
+        x = __fmaf_rn(2.0f, u01(o.x), -1.0f); y = __fmaf_rn(2.0f, u01(o.y), -1.0f); z = __fmaf_rn(2.0f, u01(o.z), -1.0f);
+        if (dot3(x, y, z, x, y, z) < 1.0f || j == 255u) return;
+    }
+}
+
+// Scatter at a hit (both integrators).  Returns false when the path ends here.
+// ctl = the control draws of this bounce: .z Russian roulette, .w metal selection.
+template <bool TRI>
+__device__ __forceinline__ bool scatter(const SceneView& sc, const Hit& h, Ray& r, int integrator, int b,
+                                        int max_depth, uint4 ctl, float4 m0, float4 m1, uint32_t pixel,
+                                        uint32_t sample, uint32_t k0, uint32_t k1, float& tr, float& tg, float& tb) {
+    bool metal;
+    if (integrator == 0) {
+        int remaining = max_depth - b;                                  // v1 counts depth down
+        if (!(remaining < 3 || u01(ctl.z) < 0.8f)) return false;
+        metal = u01(ctl.w) < m0.w;
+    } else {
+        int depth = b + 1;                                              // v2 counts depth up
+        if (depth > 3) {
+            float mc = (tr > tg) ? (tr > tb ? tr : tb) : (tg > tb ? tg : tb);
+            float p = (mc > 0.95f) ? 0.95f : mc;
+            if (p < 0.1f) p = 0.1f;
+            if (u01(ctl.z) >= p) return false;
+            float ip = __fdiv_rn(1.0f, p);
+            tr = __fmul_rn(tr, ip); tg = __fmul_rn(tg, ip); tb = __fmul_rn(tb, ip);
+        }
+        metal = m0.w > 0.0f;
+    }
+    float px = __fmaf_rn(r.dx, h.t, r.ox), py = __fmaf_rn(r.dy, h.t, r.oy), pz = __fmaf_rn(r.dz, h.t, r.oz);
+    float nx, ny, nz;
+    shading_normal<TRI>(sc, h, r, px, py, pz, nx, ny, nz);
+    float ux, uy, uz;
+    unit_sphere(pixel, sample, (uint32_t)b, k0, k1, ux, uy, uz);
+    float dx, dy, dz;
+    if (metal) {
+        float k2 = __fmul_rn(2.0f, dot3(r.dx, r.dy, r.dz, nx, ny, nz));
+        float rx = __fmaf_rn(-k2, nx, r.dx), ry = __fmaf_rn(-k2, ny, r.dy), rz = __fmaf_rn(-k2, nz, r.dz);
+        dx = __fmaf_rn(ux, m1.x, rx); dy = __fmaf_rn(uy, m1.x, ry); dz = __fmaf_rn(uz, m1.x, rz);
+    } else {
+        if (!(dot3(ux, uy, uz, nx, ny, nz) > 0.0f)) { ux = -ux; uy = -uy; uz = -uz; }
+        dx = __fadd_rn(nx, ux); dy = __fadd_rn(ny, uy); dz = __fadd_rn(nz, uz);
+    }
+    tr = __fmul_rn(tr, m0.x); tg = __fmul_rn(tg, m0.y); tb = __fmul_rn(tb, m0.z);
+    normalize3(dx, dy, dz);
+    r = make_ray(px, py, pz, dx, dy, dz);
+    return true;
+}
+
+template <bool TRI>
+__device__ __forceinline__ int material_row(const SceneView& sc, const Hit& h) {
+    if (TRI) return __float_as_int(__ldg(sc.prims + 3 * (size_t)h.slot + 1).w);
+    return h.prim;
+}
+
+// One camera sample of pixel (i,j): radiance added into (cr,cg,cb).
+template <bool TRI, bool STATS>
+__device__ __forceinline__ void radiance(const SceneView& sc, const CameraBlock& cam, int i, int j,
+                                         uint32_t pixel, uint32_t sample, int max_depth, int integrator,
+                                         uint32_t k0, uint32_t k1, double inv_w, double inv_h, float& out_r,
+                                         float& out_g, float& out_b, Counters& cnt) {
+    uint4 ctl = philox4x32_10(pixel, sample, 0u, 0u, k0, k1);
+    Ray r = camera_ray(cam, i, j, u01(ctl.x), u01(ctl.y), inv_w, inv_h);
+    float cr = 0.0f, cg = 0.0f, cb = 0.0f, tr = 1.0f, tg = 1.0f, tb = 1.0f;
+    for (int b = 0; b < max_depth; ++b) {
+        Hit h;
+        intersect<TRI, STATS>(sc, r, h, cnt);
+        if (STATS) cnt.segments += 1;
+        if (h.prim < 0) {
+            cr = __fmaf_rn(tr, sc.bg_r, cr); cg = __fmaf_rn(tg, sc.bg_g, cg); cb = __fmaf_rn(tb, sc.bg_b, cb);
+            break;
+        }
+        const float4* mp = sc.mats + 2 * (size_t)material_row<TRI>(sc, h);
+        float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+        cr = __fmaf_rn(tr, m1.y, cr); cg = __fmaf_rn(tg, m1.z, cg); cb = __fmaf_rn(tb, m1.w, cb);
+        if (b + 1 == max_depth) break;
+        if (b > 0) ctl = philox4x32_10(pixel, sample, (uint32_t)b, 0u, k0, k1);
+        if (!scatter<TRI>(sc, h, r, integrator, b, max_depth, ctl, m0, m1, pixel, sample, k0, k1, tr, tg, tb)) break;
+    }
+    out_r = cr; out_g = cg; out_b = cb;
+}
+
+__device__ __forceinline__ float resolve1(float sum, float inv_spp) {   // raytracer_core.cpp:398-409
+    float c = __fsqrt_rn(__fmul_rn(sum, inv_spp));
+    return c < 0.0f ? 0.0f : (c > 1.0f ? 1.0f : c);
+}
+
+}  // namespace b200rt

@@ -1,0 +1,270 @@
+// rt_kernels.cu -- sm_100a kernels of the render hot path and their launchers.
+// Compile with: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -lineinfo (see build.py).
+//
+// Kernel family (DESIGN.md "Kernels"):
+//   k_trace_primary  camera ray through each pixel centre -> closest hit (prim, t)      [AOV]
+//   k_trace_rays     arbitrary rays -> closest hit
+//   k_render         megakernel: spp jittered camera samples per pixel, path tracing, resolve
+//   k_untile / k_accumulate / k_tonemap_u8   framebuffer plumbing (HBM-bound elementwise)
+// All tracing kernels are persistent: grid = SMs x resident CTAs, each warp pulls one 8x4 pixel
+// block at a time from a global counter (one atomic per warp, broadcast by shuffle), so rays of a
+// warp stay spatially coherent while load imbalance between hit/miss regions is evened out.
+#include "rt_kernels.h"
+
+namespace b200rt {
+
+namespace {
+
+constexpr int kThreads = 128;
+
+struct PixelWork { int i, j, out_index; bool active; };
+
+// Decode work item `w` (one 8x4 pixel block) for this lane.
+__device__ __forceinline__ PixelWork decode_work(const TileMap& tm, int w, int lane) {
+    int bx = tm.tile_w >> 3;
+    int per_tile = bx * (tm.tile_h >> 2);
+    int k = w / per_tile;                 // local tile number
+    int sub = w - k * per_tile;
+    int sy = sub / bx, sx = sub - sy * bx;
+    int tile = tm.first_tile + k * tm.tile_stride;
+    int ty = tile / tm.tiles_x, tx = tile - ty * tm.tiles_x;
+    int lx = (sx << 3) + (lane & 7), ly = (sy << 2) + (lane >> 3);
+    PixelWork p;
+    p.i = tx * tm.tile_w + lx;
+    p.j = ty * tm.tile_h + ly;
+    p.active = p.i < tm.width && p.j < tm.height;
+    p.out_index = tm.compact ? (k * tm.tile_h + ly) * tm.tile_w + lx : p.j * tm.width + p.i;
+    return p;
+}
+
+__device__ __forceinline__ int next_work(unsigned int* counter, int lane) {
+    unsigned int w = 0;
+    if (lane == 0) w = atomicAdd(counter, 1u);
+    return (int)__shfl_sync(0xffffffffu, w, 0);
+}
+
+__device__ __forceinline__ void flush_stats(unsigned long long* d_stats, unsigned long long rays,
+                                            const Counters& c) {
+    unsigned long long v[4] = {rays, c.segments, c.nodes, c.prims};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned long long x = v[q];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(d_stats + q, x);
+    }
+}
+
+template <bool TRI, bool STATS>
+__global__ void __launch_bounds__(kThreads)
+k_trace_primary(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock cam,
+                const __grid_constant__ TileMap tm, int n_work, int32_t* __restrict__ d_prim,
+                float* __restrict__ d_t, unsigned int* counter, unsigned long long* d_stats) {
+    const int lane = threadIdx.x & 31;
+    const double inv_w = __ddiv_rn(1.0, (double)tm.width), inv_h = __ddiv_rn(1.0, (double)tm.height);
+    Counters cnt = {0, 0, 0};
+    unsigned long long rays = 0;
+    for (;;) {
+        int w = next_work(counter, lane);
+        if (w >= n_work) break;
+        PixelWork p = decode_work(tm, w, lane);
+        if (!p.active) continue;
+        Ray r = camera_ray(cam, p.i, p.j, 0.5f, 0.5f, inv_w, inv_h);
+        Hit h;
+        intersect<TRI, STATS>(sc, r, h, cnt);
+        d_prim[p.out_index] = h.prim;
+        d_t[p.out_index] = h.prim >= 0 ? h.t : 0.0f;
+        if (STATS) { rays += 1; cnt.segments += 1; }
+    }
+    if (STATS) flush_stats(d_stats, rays, cnt);
+}
+
+template <bool TRI, bool STATS>
+__global__ void __launch_bounds__(kThreads)
+k_trace_rays(const __grid_constant__ SceneView sc, const float* __restrict__ org, const float* __restrict__ dir,
+             int64_t n, int32_t* __restrict__ d_prim, float* __restrict__ d_t, unsigned long long* d_stats) {
+    Counters cnt = {0, 0, 0};
+    unsigned long long rays = 0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        float dx = dir[3 * k], dy = dir[3 * k + 1], dz = dir[3 * k + 2];
+        normalize3(dx, dy, dz);
+        Ray r = make_ray(org[3 * k], org[3 * k + 1], org[3 * k + 2], dx, dy, dz);
+        Hit h;
+        intersect<TRI, STATS>(sc, r, h, cnt);
+        d_prim[k] = h.prim;
+        d_t[k] = h.prim >= 0 ? h.t : 0.0f;
+        if (STATS) { rays += 1; cnt.segments += 1; }
+    }
+    if (STATS) flush_stats(d_stats, rays, cnt);
+}
+
+template <bool TRI, bool STATS>
+__global__ void __launch_bounds__(kThreads)
+k_render(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock cam,
+         const __grid_constant__ TileMap tm, int n_work, int spp, int max_depth, int integrator, uint32_t k0,
+         uint32_t k1, uint32_t sample_offset, int resolve, float* __restrict__ d_out, unsigned int* counter,
+         unsigned long long* d_stats) {
+    const int lane = threadIdx.x & 31;
+    const double inv_w = __ddiv_rn(1.0, (double)tm.width), inv_h = __ddiv_rn(1.0, (double)tm.height);
+    const float inv_spp = __fdiv_rn(1.0f, (float)spp);
+    Counters cnt = {0, 0, 0};
+    unsigned long long rays = 0;
+    for (;;) {
+        int w = next_work(counter, lane);
+        if (w >= n_work) break;
+        PixelWork p = decode_work(tm, w, lane);
+        if (!p.active) continue;
+        uint32_t pixel = (uint32_t)(p.j * tm.width + p.i);
+        float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+        for (int s = 0; s < spp; ++s) {
+            float cr, cg, cb;
+            radiance<TRI, STATS>(sc, cam, p.i, p.j, pixel, sample_offset + (uint32_t)s, max_depth, integrator, k0,
+                                 k1, inv_w, inv_h, cr, cg, cb, cnt);
+            sr = __fadd_rn(sr, cr); sg = __fadd_rn(sg, cg); sb = __fadd_rn(sb, cb);
+        }
+        if (STATS) rays += (unsigned long long)spp;
+        float* o = d_out + 3 * (size_t)p.out_index;
+        if (resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
+        else { o[0] = sr; o[1] = sg; o[2] = sb; }
+    }
+    if (STATS) flush_stats(d_stats, rays, cnt);
+}
+
+__global__ void k_untile(int width, int height, int tile_w, int tile_h, int tiles_x, int n_ranks, int tiles_per_rank,
+                         const float* __restrict__ tiles, float* __restrict__ frame) {
+    int64_t n = (int64_t)width * height;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        int j = (int)(p / width), i = (int)(p - (int64_t)j * width);
+        int tx = i / tile_w, ty = j / tile_h;
+        int tile = ty * tiles_x + tx;
+        int rank = tile % n_ranks, k = tile / n_ranks;
+        int64_t src = ((((int64_t)rank * tiles_per_rank + k) * tile_h + (j - ty * tile_h)) * tile_w + (i - tx * tile_w)) * 3;
+        frame[3 * p] = tiles[src]; frame[3 * p + 1] = tiles[src + 1]; frame[3 * p + 2] = tiles[src + 2];
+    }
+}
+
+// interaction.py:1311-1325 in float32: accum*w_old + batch*w_new, each product rounded.
+__global__ void k_accumulate(const float* __restrict__ batch, float* __restrict__ accum, int64_t n, float w_old,
+                             float w_new, int first) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        float b = batch[k];
+        accum[k] = first ? b : __fadd_rn(__fmul_rn(accum[k], w_old), __fmul_rn(b, w_new));
+    }
+}
+
+// interaction.py:1435-1439 then gui.py:73: x*e/(1+x*e) -> clip -> *255 -> uint8 (truncation)
+__global__ void k_tonemap_u8(const float* __restrict__ accum, uint8_t* __restrict__ out, int64_t n, float exposure) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        float x = __fmul_rn(accum[k], exposure);
+        x = __fdiv_rn(x, __fadd_rn(1.0f, x));
+        x = fminf(fmaxf(x, 0.0f), 1.0f);
+        out[k] = (uint8_t)__fmul_rn(x, 255.0f);
+    }
+}
+
+template <typename K>
+int resident_grid(K kernel, int sm_count) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
+    if (per_sm < 1) per_sm = 1;
+    return sm_count * per_sm;
+}
+
+int work_items(const TileMap& tm) { return tm.n_local_tiles * (tm.tile_w >> 3) * (tm.tile_h >> 2); }
+
+int elementwise_grid(int64_t n) {
+    int64_t g = (n + 255) / 256;
+    return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
+}
+
+}  // namespace
+
+cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
+                                 int32_t* d_prim, float* d_t, const LaunchCfg& cfg) {
+    int n_work = work_items(tm);
+    if (n_work == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
+    if (e != cudaSuccess) return e;
+    bool st = cfg.d_stats != nullptr;
+#define LAUNCH(T, S)                                                                                         \
+    {                                                                                                        \
+        int grid = resident_grid(k_trace_primary<T, S>, cfg.sm_count);                                       \
+        int need = (n_work + (kThreads / 32) - 1) / (kThreads / 32);                                         \
+        if (grid > need) grid = need;                                                                        \
+        k_trace_primary<T, S><<<grid, kThreads, 0, cfg.stream>>>(sc, cam, tm, n_work, d_prim, d_t,           \
+                                                                 cfg.d_work_counter, cfg.d_stats);           \
+    }
+    if (is_tri) { if (st) LAUNCH(true, true) else LAUNCH(true, false) }
+    else { if (st) LAUNCH(false, true) else LAUNCH(false, false) }
+#undef LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_rays(const SceneView& sc, bool is_tri, const float* d_org, const float* d_dir, int64_t n,
+                              int32_t* d_prim, float* d_t, const LaunchCfg& cfg) {
+    if (n == 0) return cudaSuccess;
+    bool st = cfg.d_stats != nullptr;
+    int64_t need = (n + kThreads - 1) / kThreads;
+#define LAUNCH(T, S)                                                                                         \
+    {                                                                                                        \
+        int grid = resident_grid(k_trace_rays<T, S>, cfg.sm_count);                                          \
+        if (grid > need) grid = (int)need;                                                                   \
+        k_trace_rays<T, S><<<grid, kThreads, 0, cfg.stream>>>(sc, d_org, d_dir, n, d_prim, d_t, cfg.d_stats); \
+    }
+    if (is_tri) { if (st) LAUNCH(true, true) else LAUNCH(true, false) }
+    else { if (st) LAUNCH(false, true) else LAUNCH(false, false) }
+#undef LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_render(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm, int spp,
+                          int max_depth, int integrator, uint64_t seed, uint32_t sample_offset, int resolve,
+                          float* d_out, const LaunchCfg& cfg) {
+    int n_work = work_items(tm);
+    if (n_work == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
+    if (e != cudaSuccess) return e;
+    bool st = cfg.d_stats != nullptr;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#define LAUNCH(T, S)                                                                                         \
+    {                                                                                                        \
+        int grid = resident_grid(k_render<T, S>, cfg.sm_count);                                              \
+        int need = (n_work + (kThreads / 32) - 1) / (kThreads / 32);                                         \
+        if (grid > need) grid = need;                                                                        \
+        k_render<T, S><<<grid, kThreads, 0, cfg.stream>>>(sc, cam, tm, n_work, spp, max_depth, integrator,   \
+                                                          k0, k1, sample_offset, resolve, d_out,             \
+                                                          cfg.d_work_counter, cfg.d_stats);                  \
+    }
+    if (is_tri) { if (st) LAUNCH(true, true) else LAUNCH(true, false) }
+    else { if (st) LAUNCH(false, true) else LAUNCH(false, false) }
+#undef LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_untile(int width, int height, int tile_w, int tile_h, int n_ranks, const float* d_tiles,
+                          float* d_frame, cudaStream_t stream) {
+    int tiles_x = (width + tile_w - 1) / tile_w, tiles_y = (height + tile_h - 1) / tile_h;
+    int n_tiles = tiles_x * tiles_y;
+    int tiles_per_rank = (n_tiles + n_ranks - 1) / n_ranks;
+    int64_t n = (int64_t)width * height;
+    if (n == 0) return cudaSuccess;
+    k_untile<<<elementwise_grid(n), 256, 0, stream>>>(width, height, tile_w, tile_h, tiles_x, n_ranks, tiles_per_rank,
+                                                      d_tiles, d_frame);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, int n_old, int n_batch,
+                              cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    double total = (double)n_old + (double)n_batch;
+    float w_old = (float)((double)n_old / total), w_new = (float)((double)n_batch / total);
+    k_accumulate<<<elementwise_grid(n), 256, 0, stream>>>(d_batch, d_accum, n, w_old, w_new, n_old == 0 ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tonemap_u8(const float* d_accum, uint8_t* d_rgb8, int64_t n, float exposure, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_tonemap_u8<<<elementwise_grid(n), 256, 0, stream>>>(d_accum, d_rgb8, n, exposure);
+    return cudaGetLastError();
+}
+
+}  // namespace b200rt

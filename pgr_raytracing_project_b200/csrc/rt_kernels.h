@@ -1,0 +1,41 @@
+// rt_kernels.h -- host-callable launchers of the sm_100a kernels (rt_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rt_device.cuh"
+
+namespace b200rt {
+
+// How a launch enumerates pixels: the frame is cut into tile_w x tile_h tiles (row-major tile
+// numbering); this launch covers tiles first_tile + k * tile_stride, k in [0, n_local_tiles).
+// Inside a tile every warp takes one 8x4 pixel block at a time from a global work counter.
+struct TileMap {
+    int width, height;
+    int tile_w, tile_h;         // multiples of 8 and 4
+    int tiles_x, n_tiles;
+    int first_tile, tile_stride, n_local_tiles;
+    int compact;                // 0: write frame layout; 1: write [k][tile_h][tile_w][...] layout
+};
+
+struct LaunchCfg {
+    cudaStream_t stream;
+    int sm_count;
+    unsigned int* d_work_counter;            // zeroed by the launcher on `stream`
+    unsigned long long* d_stats;             // [rays, segments, node_records, prim_tests] or nullptr
+};
+
+cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
+                                 int32_t* d_prim, float* d_t, const LaunchCfg& cfg);
+cudaError_t launch_trace_rays(const SceneView& sc, bool is_tri, const float* d_org, const float* d_dir, int64_t n,
+                              int32_t* d_prim, float* d_t, const LaunchCfg& cfg);
+cudaError_t launch_render(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm, int spp,
+                          int max_depth, int integrator, uint64_t seed, uint32_t sample_offset, int resolve,
+                          float* d_out, const LaunchCfg& cfg);
+cudaError_t launch_untile(int width, int height, int tile_w, int tile_h, int n_ranks, const float* d_tiles,
+                          float* d_frame, cudaStream_t stream);
+cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, int n_old, int n_batch,
+                              cudaStream_t stream);
+cudaError_t launch_tonemap_u8(const float* d_accum, uint8_t* d_rgb8, int64_t n, float exposure, cudaStream_t stream);
+
+}  // namespace b200rt

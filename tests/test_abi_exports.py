@@ -1,0 +1,48 @@
+"""CPU test: libb200rt.so loads without a GPU and exports every symbol include/b200rt.h declares
+(no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pgr_raytracing_project_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "b200rt.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    build.build()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in b200rt.h but not exported"
+    assert sorted(_lib.SYMBOLS) == names
+    lib.rt_abi_version.restype = ctypes.c_int
+    assert lib.rt_abi_version() == 1
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    L = _lib.load()
+    h = ctypes.c_void_p()
+    assert L.rt_create(0, ctypes.byref(h)) != 0
+    assert b"no CUDA device" in L.rt_last_error(None)
+    from pgr_raytracing_project_b200.context import RenderContext
+    with pytest.raises(_lib.B200RTError):
+        RenderContext()
+
+
+def test_node_layout_is_32_bytes():
+    from pgr_raytracing_project_b200.context import NODE_DTYPE
+    assert NODE_DTYPE.itemsize == 32
+    assert NODE_DTYPE.fields["a"][1] == 12 and NODE_DTYPE.fields["bmax"][1] == 16 and NODE_DTYPE.fields["b"][1] == 28
