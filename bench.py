@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 render hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric "Mrays/s and ms/frame at 1920x1080", configs[2]): C3 = synthetic
+1M-triangle random mesh (numpy default_rng(20260003)), reference median-split BVH (leaf <= 4),
+camera (0,0,30) -> origin, fov 45, 1920x1080, primary rays: one jittered camera sample per pixel,
+max_depth 1, mean -> sqrt -> clamp into the float32 RGB framebuffer.  A step is one frame.
+At N > 1 the frame is sample-range partitioned: every GPU renders its own 1 spp of the full frame
+(weak scaling: N x 2.07 M rays per step), partial sums are reduced to rank 0 over NCCL/NVLink and
+resolved there -- the reduce and the resolve are inside the timed step.
+
+One JSON line on stdout (rank 0).  `value` is device-timed with the scene resident in HBM; `e2e`
+is the same frame through the C-ABI host-buffer call (rt_set_camera + rt_render_host: camera in,
+float32 frame out to pinned host memory) timed by the host clock; `roofline` rates the dominant
+kernel against the algorithmic bytes/ray; `cpu_baseline` is the oracle port on the host cores.
+`--impl reference` times the CPU implementation alone (see reference_arm()).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+W, H = 1920, 1080
+N_TRIS = 1_000_000
+SCENE_SEED = 20260003
+RENDER_SEED = 0x5EED0003
+SPP_PER_GPU, MAX_DEPTH = 1, 1
+WORKLOAD = ("C3: synthetic 1M-triangle random mesh (default_rng(20260003), centres U[-10,10]^3, size 0.25), "
+            "1920x1080, primary rays: 1 jittered spp, max_depth 1, median-split BVH leaf<=4")
+METRIC = "primary-ray throughput at 1920x1080 (Mrays/s; ms/frame in ms_per_step)"
+BYTES_NODE, BYTES_TRI, BYTES_OUT = 32, 48, 12      # per node record, per triangle test, per ray
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def profile_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+    p = os.path.join(ROOT, "profiles", "latest_traffic.json")
+    try:
+        return json.load(open(p)).get("k_render_dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        return None
+
+
+class ClockSampler:
+    """Polls SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as exc:  # noqa: BLE001
+            self.nv = None
+            log("clock sampling unavailable:", exc)
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = get(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_scene():
+    from pgr_raytracing_project_b200 import scenes
+    return scenes.random_triangles(N_TRIS, seed=SCENE_SEED)
+
+
+# ------------------------------------------------------------------------------------ CPU arms
+def oracle_for(scene, nodes, prim_index):
+    from oracle import oracle as orc
+    o = orc.OracleScene()
+    o.load(scene, build_bvh=False)
+    o.set_bvh(nodes, prim_index)
+    o.set_camera(scene.camera.as_array(W / H))
+    return o
+
+
+def cpu_port_step(o, rect, sample_offset):
+    t0 = time.perf_counter()
+    o.render(W, H, SPP_PER_GPU, MAX_DEPTH, seed=RENDER_SEED, sample_offset=sample_offset, rect=rect)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(scene, nodes, prim_index, budget_s=12.0):
+    """Oracle port (OpenMP, all host threads) on a bounded sample of the same frame."""
+    o = oracle_for(scene, nodes, prim_index)
+    rect = (0, H // 2 - 135, W, 270)                  # centre band, a quarter of the frame
+    cpu_port_step(o, (0, H // 2 - 16, W, 32), 0)      # warm-up
+    t, rays, k = 0.0, 0, 0
+    while t < budget_s and k < 8:
+        t += cpu_port_step(o, rect, k)
+        rays += rect[2] * rect[3] * SPP_PER_GPU
+        k += 1
+    return {"value": rays / t / 1e6, "unit": "Mrays/s", "cores": o.threads, "kind": "port",
+            "sample": f"{k} x centre band {rect[2]}x{rect[3]} px of the C3 frame, oracle/rt_oracle.c near-first traversal, "
+                      f"same BVH, {o.threads} OpenMP threads, {t:.1f} s"}
+
+
+def v1_sphere_twin(budget_s=60.0):
+    """The UNMODIFIED v1 reference (oracle/_ref) on the sphere twin of C3 -- the only form of the
+    workload the reference itself can render (it has no triangles).  Bounded: 200k of the 1M
+    spheres would change the workload, so the full 1M scene is built once and one band is timed."""
+    from oracle import ref_v1
+    from pgr_raytracing_project_b200 import scenes
+    if not ref_v1.available("fast"):
+        return None
+    t0 = time.perf_counter()
+    s = scenes.random_spheres(N_TRIS, seed=SCENE_SEED)
+    rs = ref_v1.RefScene(s.center_radius, s.material8, s.object_id, s.background, flavour="fast")
+    build_s = time.perf_counter() - t0
+    cam = s.camera.as_array(W / H)
+    w2, h2 = W // 2, H // 2
+    _, ms = rs.render(cam, w2, h2, 1, 1, want_image=False)      # RayTracer::set_scene (2 BVH builds) + render
+    t0 = time.perf_counter()
+    _, ms = rs.render(cam, w2, h2, 1, 1, want_image=False)
+    rays = w2 * h2
+    return {"value": rays / (ms / 1e3) / 1e6, "unit": "Mrays/s", "cores": rs.threads, "kind": "reference",
+            "sample": f"v1 RayTracer::render({w2},{h2},spp=1,max_depth=1) on the 1M-sphere twin of C3 (r U[0.02,0.12]), "
+                      f"{rs.threads} OpenMP threads, reference flags (x86-64-v3 for native); Scene::build_bvh {rs.build_ms / 1e3:.1f} s"}
+
+
+def reference_arm(args):
+    """--impl reference: the CPU implementation of the path on the box's host cores, all threads.
+    The reference proper (v1, oracle/_ref) has no triangle primitive, so the same-config arm is the
+    oracle port (oracle/rt_oracle.c) on the C3 triangles; the v1 reference on the 1M-sphere twin is
+    reported next to it under `reference_v1_sphere_twin`."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pgr_raytracing_project_b200.context import build_bvh_host
+    scene = make_scene()
+    nodes, prim_index = build_bvh_host(scene.vertices, True)
+    o = oracle_for(scene, nodes, prim_index)
+    band = (0, H // 2 - 16, W, 32)
+    cpu_port_step(o, band, 0)
+    per_row = cpu_port_step(o, band, 0) / 32.0
+    # size the per-step sample so that (steps + warmup) samples take <= ~120 s
+    rows = int(max(8, min(H, 120.0 / max(args.steps + args.warmup, 1) / per_row)))
+    rows -= rows % 4
+    rect = (0, (H - rows) // 2, W, rows)
+    for k in range(args.warmup):
+        cpu_port_step(o, rect, k)
+    t = 0.0
+    for k in range(args.steps):
+        t += cpu_port_step(o, rect, args.warmup + k)
+    rays = rect[2] * rect[3] * SPP_PER_GPU * args.steps
+    value = rays / t / 1e6
+    sample = (f"each step = centre band {rect[2]}x{rect[3]} px of the C3 frame ({rect[3] / H:.0%} of a frame), "
+              f"{o.threads} OpenMP threads")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
+        "ms_per_frame_extrapolated": t / args.steps * 1e3 * H / rect[3],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "width": W, "height": H, "spp": SPP_PER_GPU, "max_depth": MAX_DEPTH},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": o.threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    try:
+        out["reference_v1_sphere_twin"] = v1_sphere_twin()
+    except Exception as exc:  # noqa: BLE001
+        out["reference_v1_sphere_twin"] = {"unavailable": str(exc)}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pgr_raytracing_project_b200.context import RenderContext
+    from pgr_raytracing_project_b200.multigpu import DistributedRenderer
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    scene = make_scene()
+    ctx = RenderContext(local_rank)
+    t0 = time.perf_counter()
+    ctx.set_scene(scene)
+    build_s = time.perf_counter() - t0
+    cam = scene.camera
+    ctx.set_camera(cam.position, cam.target, cam.up, cam.fov)
+    nodes, prim_index = ctx.get_bvh()
+    renderer = DistributedRenderer(ctx, rank, world, mode="samples")
+    spp_total = SPP_PER_GPU * world
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=ctx.device)       # 512 MiB > 126 MB L2
+
+    def step(k):
+        return renderer.render(W, H, spp_total, MAX_DEPTH, RENDER_SEED, k * spp_total)
+
+    # exact work counters of the timed steps (instrumented kernel variant, outside the timed region)
+    ctx.set_option("stats", 1)
+    ctx.reset_stats()
+    for k in range(args.steps):
+        first = k * spp_total + rank * SPP_PER_GPU
+        ctx.render_sum(W, H, SPP_PER_GPU, MAX_DEPTH, RENDER_SEED, first, out=renderer._buf("part", (H, W, 3)))
+    st = ctx.stats()
+    ctx.set_option("stats", 0)
+    rays_per_launch = st["rays"] / args.steps
+    nodes_per_ray = st["node_records"] / st["rays"]
+    tris_per_ray = st["prim_tests"] / st["rays"]
+    bytes_per_ray = BYTES_NODE * nodes_per_ray + BYTES_TRI * tris_per_ray + BYTES_OUT
+
+    for k in range(args.warmup):
+        flush.zero_()
+        step(k)
+    torch.cuda.synchronize()
+
+    # ---- device-timed region: K steps, CUDA events around each step on the launching stream,
+    # L2 flushed (512 MiB memset) between steps outside the event pairs
+    ctx.reset_stats()
+    sampler = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record()
+        step(k)
+        ev[k][1].record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.stats()["launches"]
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=ctx.device)
+    n_launch = torch.tensor([launches], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_launch, op=dist.ReduceOp.SUM)
+    total_ms = float(total_ms.item())
+    rays_total = W * H * spp_total * args.steps
+    value = rays_total / (total_ms / 1e3) / 1e6
+
+    # ---- dominant kernel alone (k_render on this rank), for the roofline
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    part = renderer._buf("part", (H, W, 3))
+    for k in range(args.steps):
+        flush.zero_()
+        kev[k][0].record()
+        ctx.render_sum(W, H, SPP_PER_GPU, MAX_DEPTH, RENDER_SEED, k * spp_total + rank * SPP_PER_GPU, out=part)
+        kev[k][1].record()
+    torch.cuda.synchronize()
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    peak, peak_src = measured_peaks()
+    achieved = rays_per_launch * bytes_per_ray / (kernel_ms / 1e3) / 1e9
+    # warm-L2 figure for context (no flush between launches)
+    torch.cuda.synchronize()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    for k in range(args.steps):
+        ctx.render_sum(W, H, SPP_PER_GPU, MAX_DEPTH, RENDER_SEED, k, out=part)
+    w1.record()
+    torch.cuda.synchronize()
+    warm_ms = w0.elapsed_time(w1) / args.steps
+
+    # ---- end to end: host buffers through the C-ABI call, host clock, copies inside
+    host = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+    host_np = host.numpy()
+    part_host = None
+
+    def e2e_step(k):
+        ctx.set_camera(cam.position, cam.target, cam.up, cam.fov)          # camera in (112-byte block)
+        if world == 1:
+            ctx.render_host(W, H, SPP_PER_GPU, MAX_DEPTH, RENDER_SEED, k, out=host_np)   # frame out
+        else:
+            frame = step(k)
+            if rank == 0:
+                host.copy_(frame, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for k in range(3):
+        e2e_step(k)
+    barrier()
+    torch.cuda.synchronize()
+    e2e_s = 0.0
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step(k)
+        e2e_s += time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device=ctx.device)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = rays_total / float(e2e_t.item()) / 1e6
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD, "width": W, "height": H, "spp_per_gpu": SPP_PER_GPU, "spp_total": spp_total,
+                "max_depth": MAX_DEPTH, "n_triangles": N_TRIS, "bvh_nodes": int(len(nodes)),
+                "partition": "single GPU" if world == 1 else
+                             f"sample-range: 1 spp of the full frame per GPU, NCCL reduce(SUM) to rank 0 + resolve, inside the step",
+                "l2": "scene+BVH = 64 MB < 126 MB L2, so a 512 MiB memset flushes L2 before every timed step "
+                      "(outside the CUDA-event pairs)",
+                "host_bvh_build_plus_upload_s": round(build_s, 2),
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 112, "d2h_bytes_per_step": W * H * 3 * 4,
+                    "ms_per_step": float(e2e_t.item()) / args.steps * 1e3,
+                    "api": "rt_set_camera + rt_render_host (pinned host framebuffer)" if world == 1 else
+                           "DistributedRenderer.render + copy of the resolved frame to pinned host memory on rank 0"},
+            "gpu_launches": int(n_launch.item()),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": profile_traffic(), "kernel": "k_render<TRI> (megakernel: raygen + BVH traversal + shade + resolve)",
+                "kernel_ms": kernel_ms, "kernel_ms_warm_l2": warm_ms, "peak_source": peak_src,
+                "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                "rays_per_launch": rays_per_launch,
+                "note": "algorithmic bytes: every 32-B node record and 48-B triangle fetched counts, no credit for cache "
+                        "hits; the working set is L2-resident, so this is a traversal-rate figure rated against HBM "
+                        "copy bandwidth",
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                out["cpu_baseline"] = cpu_baseline(scene, nodes, prim_index)
+            except Exception as exc:  # noqa: BLE001
+                out["cpu_baseline"] = {"unavailable": str(exc)}
+        print(json.dumps(out), flush=True)
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -126,6 +126,12 @@ int rt_render(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64
 int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int first_tile,
                     int tile_stride, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
                     int resolve, float* d_out, void* stream);
+/* Full frame, raw radiance sums (no mean / gamma / clamp): the per-rank partial of a sample-range
+ * partition; sum the partials (e.g. ncclReduce) and finish with rt_resolve. */
+int rt_render_sum(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed,
+                  uint32_t sample_offset, float* d_out, void* stream);
+/* mean over spp_total -> sqrt gamma -> clamp [0,1] (cpp_raytracer/raytracer_core.cpp:398-409). */
+int rt_resolve(rt_ctx* ctx, const float* d_sum, float* d_out, int64_t n_floats, int spp_total, void* stream);
 /* Scatter gathered compact tile buffers [rank][k][tile_h][tile_w][3] back into a H*W*3 frame. */
 int rt_untile(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int n_ranks,
               const float* d_tiles, float* d_frame, void* stream);

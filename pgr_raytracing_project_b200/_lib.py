@@ -14,7 +14,7 @@ SYMBOLS = [
     "rt_set_background", "rt_build_bvh", "rt_get_bvh", "rt_set_bvh", "rt_set_camera", "rt_get_camera_block",
     "rt_trace_primary", "rt_trace_rays", "rt_select_object", "rt_render", "rt_render_tiles", "rt_untile",
     "rt_render_host", "rt_accumulate", "rt_tonemap_u8", "rt_set_option", "rt_get_option", "rt_get_stats",
-    "rt_reset_stats", "rt_build_bvh_host",
+    "rt_reset_stats", "rt_build_bvh_host", "rt_render_sum", "rt_resolve",
 ]
 
 
@@ -64,6 +64,8 @@ def load():
         "rt_trace_rays": (ci, [vp, vp, vp, i64, vp, vp, vp]),
         "rt_select_object": (ci, [vp, C.c_double, C.c_double, ci, ci, ip]),
         "rt_render": (ci, [vp, ci, ci, ci, ci, u64, u32, vp, vp]),
+        "rt_render_sum": (ci, [vp, ci, ci, ci, ci, u64, u32, vp, vp]),
+        "rt_resolve": (ci, [vp, vp, vp, i64, ci, vp]),
         "rt_render_tiles": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, u64, u32, ci, vp, vp]),
         "rt_untile": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, vp]),
         "rt_render_host": (ci, [vp, ci, ci, ci, ci, u64, u32, vp]),

@@ -173,6 +173,21 @@ class RenderContext:
                                   out.data_ptr(), self._stream()))
         return out
 
+    def render_sum(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Raw radiance sums of samples [sample_offset, sample_offset + spp) (sample-range partials)."""
+        if out is None:
+            out = torch.empty((height, width, 3), dtype=torch.float32, device=self.device)
+        self._ck(self.L.rt_render_sum(self.h, width, height, spp, max_depth, C.c_uint64(seed), C.c_uint32(sample_offset),
+                                      out.data_ptr(), self._stream()))
+        return out
+
+    def resolve(self, summed: torch.Tensor, spp_total: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty_like(summed)
+        self._ck(self.L.rt_resolve(self.h, summed.data_ptr(), out.data_ptr(), summed.numel(), int(spp_total), self._stream()))
+        return out
+
     def render_tiles(self, width: int, height: int, tile_w: int, tile_h: int, first_tile: int, tile_stride: int,
                      spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0, resolve: bool = True,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -451,9 +451,8 @@ int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, 
     return 0;
 }
 
-int rt_render(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
-              float* d_out, void* stream) {
-    if (!ctx) return 1;
+static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
+                        int resolve, float* d_out, void* stream) {
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (int rc = check_frame(ctx, width, height)) return rc;
     if (spp <= 0 || max_depth < 0 || !d_out) return fail(ctx, "rt_render: bad arguments");
@@ -462,8 +461,30 @@ int rt_render(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64
     ctx->aspect = (double)width / height;
     CameraBlock cam = camera_block(ctx, ctx->aspect);
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, full_frame_map(width, height), spp, max_depth, ctx->integrator,
-                     seed, sample_offset, 1, d_out, launch_cfg(ctx, stream)));
+                     seed, sample_offset, resolve, d_out, launch_cfg(ctx, stream)));
     ctx->launches += 1;
+    return 0;
+}
+
+int rt_render(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
+              float* d_out, void* stream) {
+    if (!ctx) return 1;
+    return render_frame(ctx, width, height, spp, max_depth, seed, sample_offset, 1, d_out, stream);
+}
+
+int rt_render_sum(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
+                  float* d_out, void* stream) {
+    if (!ctx) return 1;
+    return render_frame(ctx, width, height, spp, max_depth, seed, sample_offset, 0, d_out, stream);
+}
+
+int rt_resolve(rt_ctx* ctx, const float* d_sum, float* d_out, int64_t n, int spp_total, void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || spp_total <= 0 || (n > 0 && (!d_sum || !d_out))) return fail(ctx, "rt_resolve: bad arguments");
+    DeviceGuard g(ctx->device);
+    CK(launch_resolve(d_sum, d_out, n, spp_total, (cudaStream_t)stream));
+    if (n) ctx->launches += 1;
     return 0;
 }
 

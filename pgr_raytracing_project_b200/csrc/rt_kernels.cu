@@ -142,6 +142,11 @@ __global__ void k_untile(int width, int height, int tile_w, int tile_h, int tile
     }
 }
 
+__global__ void k_resolve(const float* __restrict__ sum, float* __restrict__ out, int64_t n, float inv_spp) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        out[k] = resolve1(sum[k], inv_spp);
+}
+
 // interaction.py:1311-1325 in float32: accum*w_old + batch*w_new, each product rounded.
 __global__ void k_accumulate(const float* __restrict__ batch, float* __restrict__ accum, int64_t n, float w_old,
                              float w_new, int first) {
@@ -249,6 +254,12 @@ cudaError_t launch_untile(int width, int height, int tile_w, int tile_h, int n_r
     if (n == 0) return cudaSuccess;
     k_untile<<<elementwise_grid(n), 256, 0, stream>>>(width, height, tile_w, tile_h, tiles_x, n_ranks, tiles_per_rank,
                                                       d_tiles, d_frame);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve(const float* d_sum, float* d_out, int64_t n, int spp_total, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_resolve<<<elementwise_grid(n), 256, 0, stream>>>(d_sum, d_out, n, 1.0f / (float)spp_total);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,7 @@ cudaError_t launch_render(const SceneView& sc, bool is_tri, const CameraBlock& c
                           float* d_out, const LaunchCfg& cfg);
 cudaError_t launch_untile(int width, int height, int tile_w, int tile_h, int n_ranks, const float* d_tiles,
                           float* d_frame, cudaStream_t stream);
+cudaError_t launch_resolve(const float* d_sum, float* d_out, int64_t n, int spp_total, cudaStream_t stream);
 cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, int n_old, int n_batch,
                               cudaStream_t stream);
 cudaError_t launch_tonemap_u8(const float* d_accum, uint8_t* d_rgb8, int64_t n, float exposure, cudaStream_t stream);
