@@ -152,8 +152,10 @@ int rt_tonemap_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
 
 /* ---- options and counters.  Options: "integrator" 0 = v1 semantics (default; the generation
  * that runs: RR `depth<3 || rand<0.8` unweighted, metal chosen with probability metallic),
- * 1 = v2 semantics (raytracer_core.cpp:317-347); "stats" 0/1; "kernel" traversal variant
- * (0 = default); "wavefront" 0/1. */
+ * 1 = v2 semantics (raytracer_core.cpp:317-347); "stats" 0/1; "kernel" 0 = persistent path
+ * kernel with lane-level continuation (default), 1 = simple one-pixel-per-thread megakernel (same
+ * results, kept for A/B profiling); "refill" 1..32 = lane count below which a warp of kernel 0
+ * leaves the traversal loop to shade / refill (default 24). */
 int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);
 int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value);
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);   /* synchronises the device */

@@ -49,7 +49,7 @@ struct rt_ctx {
     double fov = 45.0, aspect = 1.333;
 
     // options
-    int integrator = 0, stats = 0, kernel = 0, wavefront = 0;
+    int integrator = 0, stats = 0, kernel = 0, refill = 24;
 
     unsigned int* d_work_counter = nullptr;
     unsigned long long* d_stats = nullptr;   // rays, segments, node_records, prim_tests
@@ -181,6 +181,8 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream) {
     cfg.sm_count = c->sm_count;
     cfg.d_work_counter = c->d_work_counter;
     cfg.d_stats = c->stats ? c->d_stats : nullptr;
+    cfg.variant = c->kernel;
+    cfg.refill_below = c->refill;
     return cfg;
 }
 
@@ -544,8 +546,8 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     std::string k(name);
     if (k == "integrator") { if (value != 0 && value != 1) return fail(ctx, "integrator must be 0 (v1) or 1 (v2)"); ctx->integrator = (int)value; }
     else if (k == "stats") ctx->stats = value != 0;
-    else if (k == "kernel") ctx->kernel = (int)value;
-    else if (k == "wavefront") ctx->wavefront = value != 0;
+    else if (k == "kernel") { if (value != 0 && value != 1) return fail(ctx, "kernel must be 0 (k_path) or 1 (simple megakernel)"); ctx->kernel = (int)value; }
+    else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
     else return fail(ctx, "rt_set_option: unknown option '" + k + "'");
     return 0;
 }
@@ -557,7 +559,7 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     if (k == "integrator") *value = ctx->integrator;
     else if (k == "stats") *value = ctx->stats;
     else if (k == "kernel") *value = ctx->kernel;
-    else if (k == "wavefront") *value = ctx->wavefront;
+    else if (k == "refill") *value = ctx->refill;
     else if (k == "sm_count") *value = ctx->sm_count;
     else if (k == "bvh_depth") *value = ctx->bvh_depth;
     else if (k == "n_prims") *value = ctx->n;

@@ -218,6 +218,71 @@ __device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit
     }
 }
 
+// ------------------------------------------------------------------------------- resumable traversal
+// The same walk as intersect(), cut into a per-lane state (Trav + a local-memory stack) so that a
+// warp can leave the traversal loop when too few of its lanes still have work, shade / refill the
+// finished lanes, and come back.  Node codes: >= 0 internal (index of the child pair), <= -2 leaf
+// (~((first_slot << 3) | count)), kDone = -1.  The per-ray visiting order is exactly intersect()'s.
+constexpr int kDone = -1;
+
+struct Trav { int cur; int sp; Hit h; };
+
+__device__ __forceinline__ int node_code(int a, int b) { return b == 0 ? a : ~((a << 3) | b); }
+
+__device__ __forceinline__ void trav_pop(Trav& tv, const int* stack_code, const float* stack_tn) {
+    while (tv.sp > 0) {
+        --tv.sp;
+        if (stack_tn[tv.sp] <= tv.h.t) { tv.cur = stack_code[tv.sp]; return; }
+    }
+    tv.cur = kDone;
+}
+
+template <bool STATS>
+__device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Trav& tv, Counters& cnt) {
+    tv.h.t = kTMax; tv.h.prim = -1; tv.h.slot = -1;
+    tv.sp = 0; tv.cur = kDone;
+    if (sc.n_nodes == 0) return;
+    float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
+    float tn;
+    if (STATS) cnt.nodes += 1;
+    if (box_hit(lo, hi, r, kTMin, tv.h.t, tn)) tv.cur = node_code(__float_as_int(lo.w), __float_as_int(hi.w));
+}
+
+// Runs the warp's traversals until fewer than `min_active` lanes still have work (warp-uniform call).
+template <bool TRI, bool STATS>
+__device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav& tv, int* stack_code,
+                                         float* stack_tn, int min_active, Counters& cnt) {
+    for (;;) {
+        while (tv.cur >= 0) {                                   // internal nodes
+            const float4* p = sc.nodes + 2 * (size_t)tv.cur;
+            float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
+            if (STATS) cnt.nodes += 2;
+            float tl, tr;
+            bool hl = box_hit(l0, l1, r, kTMin, tv.h.t, tl);
+            bool hr = box_hit(r0, r1, r, kTMin, tv.h.t, tr);
+            int lc = node_code(__float_as_int(l0.w), __float_as_int(l1.w));
+            int rc = node_code(__float_as_int(r0.w), __float_as_int(r1.w));
+            if (hl && hr) {
+                if (tr < tl) { int c = lc; lc = rc; rc = c; float tf = tl; tl = tr; tr = tf; }
+                stack_code[tv.sp] = rc; stack_tn[tv.sp] = tr; ++tv.sp;
+                tv.cur = lc;
+            } else if (hl) tv.cur = lc;
+            else if (hr) tv.cur = rc;
+            else trav_pop(tv, stack_code, stack_tn);
+        }
+        if (tv.cur < kDone) {                                   // one leaf
+            int code = ~tv.cur;
+            int first = code >> 3, count = code & 7;
+            for (int k = 0; k < count; ++k) {
+                if (STATS) cnt.prims += 1;
+                test_prim<TRI>(sc, first + k, r, tv.h);
+            }
+            trav_pop(tv, stack_code, stack_tn);
+        }
+        if (__popc(__ballot_sync(0xffffffffu, tv.cur != kDone)) < min_active) break;
+    }
+}
+
 // ------------------------------------------------------------------------------- shading
 template <bool TRI>
 __device__ __forceinline__ void shading_normal(const SceneView& sc, const Hit& h, const Ray& r, float px,

@@ -129,6 +129,127 @@ k_render(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlo
     if (STATS) flush_stats(d_stats, rays, cnt);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_path: persistent-thread path tracer with lane-level continuation (the default kernel).
+// Work unit = one pixel (all of its samples, in order, so the sample sum is deterministic).  Each
+// lane is a small state machine {NONE, START, TRAV, SHADE}.  A warp traverses until fewer than
+// `refill_below` of its lanes still traverse; the finished lanes are then shaded (next bounce or
+// next sample) or refilled with new pixels from the global counter -- one atomic per refill, the
+// requesting lanes ranked with ballot/popc -- and the warp re-enters the traversal loop with the
+// unfinished lanes resuming exactly where they were.  AOV = true is the primary-hit query
+// (pixel-centre ray, writes prim/t instead of radiance).
+enum { PH_NONE = 0, PH_START = 1, PH_TRAV = 2, PH_SHADE = 3 };
+
+template <bool TRI, bool STATS, bool AOV>
+__global__ void __launch_bounds__(kThreads)
+k_path(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock cam,
+       const __grid_constant__ TileMap tm, int n_tasks, int spp, int max_depth, int integrator, uint32_t k0,
+       uint32_t k1, uint32_t sample_offset, int resolve, int refill_below, float* __restrict__ d_out,
+       int32_t* __restrict__ d_prim, float* __restrict__ d_t, unsigned int* counter, unsigned long long* d_stats) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const double inv_w = __ddiv_rn(1.0, (double)tm.width), inv_h = __ddiv_rn(1.0, (double)tm.height);
+    const float inv_spp = __fdiv_rn(1.0f, (float)spp);
+    int stack_code[kStackDepth];
+    float stack_tn[kStackDepth];
+    Trav tv;
+    tv.cur = kDone; tv.sp = 0; tv.h.t = kTMax; tv.h.prim = -1; tv.h.slot = -1;
+    Counters cnt = {0, 0, 0};
+    unsigned long long rays = 0;
+    int phase = PH_NONE;
+    int pi = 0, pj = 0, out_index = 0, s = 0, b = 0;
+    uint32_t pixel = 0, ctl_z = 0, ctl_w = 0;
+    Ray r = make_ray(0.f, 0.f, 0.f, 0.f, 0.f, 1.f);
+    float tr = 1.f, tg = 1.f, tb = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+    bool pool_empty = false;
+
+    for (;;) {
+        // ---- A: lanes outside the traversal loop: start a sample / shade a finished segment
+        while (phase == PH_START || phase == PH_SHADE) {
+            if (phase == PH_START) {
+                float jx = 0.5f, jy = 0.5f;
+                if (!AOV) {
+                    uint4 ctl = philox4x32_10(pixel, sample_offset + (uint32_t)s, 0u, 0u, k0, k1);
+                    jx = u01(ctl.x); jy = u01(ctl.y); ctl_z = ctl.z; ctl_w = ctl.w;
+                }
+                r = camera_ray(cam, pi, pj, jx, jy, inv_w, inv_h);
+                tr = tg = tb = 1.0f; cr = cg = cb = 0.0f; b = 0;
+                if (STATS) rays += 1;
+                trav_begin<STATS>(sc, r, tv, cnt);
+                phase = tv.cur != kDone ? PH_TRAV : PH_SHADE;
+            } else {
+                if (STATS) cnt.segments += 1;
+                if (AOV) {
+                    d_prim[out_index] = tv.h.prim;
+                    d_t[out_index] = tv.h.prim >= 0 ? tv.h.t : 0.0f;
+                    phase = PH_NONE;
+                    break;
+                }
+                bool path_end = true;
+                if (tv.h.prim < 0) {
+                    cr = __fmaf_rn(tr, sc.bg_r, cr); cg = __fmaf_rn(tg, sc.bg_g, cg); cb = __fmaf_rn(tb, sc.bg_b, cb);
+                } else {
+                    const float4* mp = sc.mats + 2 * (size_t)material_row<TRI>(sc, tv.h);
+                    float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                    cr = __fmaf_rn(tr, m1.y, cr); cg = __fmaf_rn(tg, m1.z, cg); cb = __fmaf_rn(tb, m1.w, cb);
+                    if (b + 1 < max_depth) {
+                        uint32_t sample = sample_offset + (uint32_t)s;
+                        uint4 ctl = make_uint4(0u, 0u, ctl_z, ctl_w);
+                        if (b > 0) ctl = philox4x32_10(pixel, sample, (uint32_t)b, 0u, k0, k1);
+                        if (scatter<TRI>(sc, tv.h, r, integrator, b, max_depth, ctl, m0, m1, pixel, sample, k0, k1, tr, tg, tb)) {
+                            ++b;
+                            trav_begin<STATS>(sc, r, tv, cnt);
+                            phase = tv.cur != kDone ? PH_TRAV : PH_SHADE;
+                            path_end = false;
+                        }
+                    }
+                }
+                if (path_end) {
+                    sr = __fadd_rn(sr, cr); sg = __fadd_rn(sg, cg); sb = __fadd_rn(sb, cb);
+                    if (++s < spp) phase = PH_START;
+                    else {
+                        float* o = d_out + 3 * (size_t)out_index;
+                        if (resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
+                        else { o[0] = sr; o[1] = sg; o[2] = sb; }
+                        phase = PH_NONE;
+                    }
+                }
+            }
+        }
+        // ---- B: refill idle lanes with new pixels (warp-aggregated atomic)
+        unsigned need = __ballot_sync(0xffffffffu, phase == PH_NONE);
+        if (need != 0u && !pool_empty) {
+            int n_need = __popc(need);
+            int leader = __ffs(need) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(counter, (unsigned)n_need);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (phase == PH_NONE) {
+                unsigned idx = base + (unsigned)__popc(need & lt_mask);
+                if (idx < (unsigned)n_tasks) {
+                    PixelWork p = decode_work(tm, (int)(idx >> 5), (int)(idx & 31u));
+                    if (p.active) {
+                        pi = p.i; pj = p.j; out_index = p.out_index;
+                        pixel = (uint32_t)(p.j * tm.width + p.i);
+                        s = 0; sr = sg = sb = 0.0f;
+                        phase = PH_START;
+                    }
+                }
+            }
+            if (base + (unsigned)n_need >= (unsigned)n_tasks) pool_empty = true;
+            continue;
+        }
+        // ---- C: traverse
+        unsigned act = __ballot_sync(0xffffffffu, phase == PH_TRAV);
+        if (act == 0u) break;                      // every lane idle and the pool is empty
+        // leave the loop again once a quarter (32 - refill_below in 32) of the lanes that entered are done
+        int min_active = (__popc(act) * refill_below) >> 5;
+        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, cnt);
+        if (phase == PH_TRAV && tv.cur == kDone) phase = PH_SHADE;
+    }
+    if (STATS) flush_stats(d_stats, rays, cnt);
+}
+
 __global__ void k_untile(int width, int height, int tile_w, int tile_h, int tiles_x, int n_ranks, int tiles_per_rank,
                          const float* __restrict__ tiles, float* __restrict__ frame) {
     int64_t n = (int64_t)width * height;
@@ -183,6 +304,24 @@ int elementwise_grid(int64_t n) {
 
 }  // namespace
 
+namespace {
+
+template <bool TRI, bool STATS, bool AOV>
+cudaError_t launch_path(const SceneView& sc, const CameraBlock& cam, const TileMap& tm, int spp, int max_depth,
+                        int integrator, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out,
+                        int32_t* d_prim, float* d_t, const LaunchCfg& cfg) {
+    int n_work = work_items(tm);
+    int grid = resident_grid(k_path<TRI, STATS, AOV>, cfg.sm_count);
+    int need = (n_work + (kThreads / 32) - 1) / (kThreads / 32);
+    if (grid > need) grid = need;
+    k_path<TRI, STATS, AOV><<<grid, kThreads, 0, cfg.stream>>>(
+        sc, cam, tm, n_work * 32, spp, max_depth, integrator, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset,
+        resolve, cfg.refill_below, d_out, d_prim, d_t, cfg.d_work_counter, cfg.d_stats);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
                                  int32_t* d_prim, float* d_t, const LaunchCfg& cfg) {
     int n_work = work_items(tm);
@@ -190,6 +329,12 @@ cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraB
     cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
     if (e != cudaSuccess) return e;
     bool st = cfg.d_stats != nullptr;
+    if (cfg.variant == 0) {
+        if (is_tri) return st ? launch_path<true, true, true>(sc, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t, cfg)
+                              : launch_path<true, false, true>(sc, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t, cfg);
+        return st ? launch_path<false, true, true>(sc, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t, cfg)
+                  : launch_path<false, false, true>(sc, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t, cfg);
+    }
 #define LAUNCH(T, S)                                                                                         \
     {                                                                                                        \
         int grid = resident_grid(k_trace_primary<T, S>, cfg.sm_count);                                       \
@@ -229,6 +374,12 @@ cudaError_t launch_render(const SceneView& sc, bool is_tri, const CameraBlock& c
     cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
     if (e != cudaSuccess) return e;
     bool st = cfg.d_stats != nullptr;
+    if (cfg.variant == 0) {
+        if (is_tri) return st ? launch_path<true, true, false>(sc, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg)
+                              : launch_path<true, false, false>(sc, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg);
+        return st ? launch_path<false, true, false>(sc, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg)
+                  : launch_path<false, false, false>(sc, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg);
+    }
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #define LAUNCH(T, S)                                                                                         \
     {                                                                                                        \

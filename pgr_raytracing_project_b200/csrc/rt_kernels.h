@@ -23,6 +23,8 @@ struct LaunchCfg {
     int sm_count;
     unsigned int* d_work_counter;            // zeroed by the launcher on `stream`
     unsigned long long* d_stats;             // [rays, segments, node_records, prim_tests] or nullptr
+    int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel
+    int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes
 };
 
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,

@@ -20,10 +20,13 @@ pytestmark = pytest.mark.gpu
 REL_T = 1e-5
 
 
-@pytest.fixture(scope="module")
-def ctx():
+@pytest.fixture(scope="module", params=[0, 1], ids=["k_path", "simple"])
+def ctx(request):
+    """Both tracing kernels must meet every bar: 0 = persistent path kernel with lane-level
+    continuation (default), 1 = simple one-pixel-per-thread megakernel."""
     from pgr_raytracing_project_b200.context import RenderContext
     c = RenderContext(0)
+    c.set_option("kernel", request.param)
     yield c
     c.close()
 
