@@ -55,6 +55,9 @@ struct rt_ctx {
     unsigned long long* d_stats = nullptr;   // rays, segments, node_records, prim_tests
     uint64_t launches = 0;
 
+    WaveBuffers wave = {{nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr, 0};
+    int wave_depth = 0;                      // counters sized for this max_depth
+
     float* d_fb = nullptr;                   // rt_render_host framebuffer
     size_t fb_floats = 0;
     int32_t* d_pick = nullptr;               // rt_select_object scratch: org3 dir3 | prim | t
@@ -114,6 +117,34 @@ CameraBlock camera_block(const rt_ctx* c, double aspect) {
 }
 
 int ensure_bvh(rt_ctx* ctx);
+
+void free_wave(rt_ctx* c) {
+    for (int k = 0; k < 2; ++k) { cudaFree(c->wave.ray_o[k]); cudaFree(c->wave.ray_d[k]); c->wave.ray_o[k] = c->wave.ray_d[k] = nullptr; }
+    cudaFree(c->wave.hit); cudaFree(c->wave.path_thr); cudaFree(c->wave.path_rad); cudaFree(c->wave.counters);
+    c->wave.hit = c->wave.path_thr = c->wave.path_rad = nullptr; c->wave.counters = nullptr;
+    c->wave.capacity = 0; c->wave_depth = 0;
+}
+
+// Wavefront buffers: grow-only, sized for min(paths of the call, 8 Mi) paths per wave.
+int ensure_wave(rt_ctx* ctx, int64_t n_tasks, int spp, int max_depth) {
+    int64_t want = n_tasks * (int64_t)spp;
+    const int64_t kCap = (int64_t)8 << 20;
+    if (want > kCap) want = n_tasks > kCap ? kCap : (kCap / n_tasks) * n_tasks;
+    if (want < 1024) want = 1024;
+    if (want <= ctx->wave.capacity && max_depth <= ctx->wave_depth) return 0;
+    int64_t cap = want > ctx->wave.capacity ? want : ctx->wave.capacity;
+    int depth = max_depth > ctx->wave_depth ? max_depth : ctx->wave_depth;
+    cudaDeviceSynchronize();
+    free_wave(ctx);
+    size_t b = (size_t)cap * sizeof(float4);
+    for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&ctx->wave.ray_o[k], b)); CK(cudaMalloc(&ctx->wave.ray_d[k], b)); }
+    CK(cudaMalloc(&ctx->wave.hit, b)); CK(cudaMalloc(&ctx->wave.path_thr, b)); CK(cudaMalloc(&ctx->wave.path_rad, b));
+    CK(cudaMalloc(&ctx->wave.counters, sizeof(unsigned int) * 2 * (depth + 2)));
+    ctx->wave.capacity = (int)cap; ctx->wave_depth = depth;
+    return 0;
+}
+
+int64_t task_count(const TileMap& tm) { return (int64_t)tm.n_local_tiles * (tm.tile_w >> 3) * (tm.tile_h >> 2) * 32; }
 
 // Host scene + BVH -> device arrays in leaf order.
 int ensure_device(rt_ctx* ctx) {
@@ -243,6 +274,7 @@ void rt_destroy(rt_ctx* ctx) {
         DeviceGuard g(ctx->device);
         cudaDeviceSynchronize();
         free_device_scene(ctx);
+        free_wave(ctx);
         cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick);
     }
     delete ctx;
@@ -383,8 +415,16 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
     if (int rc = ensure_device(ctx)) return rc;
     ctx->aspect = (double)width / height;            // RayTracer::render, old/raytracer_core copy.cpp:259
     CameraBlock cam = camera_block(ctx, ctx->aspect);
-    CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, full_frame_map(width, height), d_prim, d_t,
-                            launch_cfg(ctx, stream)));
+    TileMap tm = full_frame_map(width, height);
+    if (ctx->kernel == 2) {
+        if (int rc = ensure_wave(ctx, task_count(tm), 1, 1)) return rc;
+        int nl = 0;
+        CK(launch_wavefront(scene_view(ctx), ctx->is_tri, true, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t,
+                            launch_cfg(ctx, stream), ctx->wave, &nl));
+        ctx->launches += nl;
+        return 0;
+    }
+    CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, tm, d_prim, d_t, launch_cfg(ctx, stream)));
     ctx->launches += 1;
     return 0;
 }
@@ -447,6 +487,14 @@ int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, 
     tm.first_tile = first_tile; tm.tile_stride = tile_stride;
     tm.n_local_tiles = first_tile < tm.n_tiles ? (tm.n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
     tm.compact = 1;
+    if (ctx->kernel == 2 && tm.n_local_tiles) {
+        if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
+        int nl = 0;
+        CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
+                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream), ctx->wave, &nl));
+        ctx->launches += nl;
+        return 0;
+    }
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, launch_cfg(ctx, stream)));
     if (tm.n_local_tiles) ctx->launches += 1;
@@ -462,8 +510,17 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
     if (int rc = ensure_device(ctx)) return rc;
     ctx->aspect = (double)width / height;
     CameraBlock cam = camera_block(ctx, ctx->aspect);
-    CK(launch_render(scene_view(ctx), ctx->is_tri, cam, full_frame_map(width, height), spp, max_depth, ctx->integrator,
-                     seed, sample_offset, resolve, d_out, launch_cfg(ctx, stream)));
+    TileMap tm = full_frame_map(width, height);
+    if (ctx->kernel == 2) {
+        if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
+        int nl = 0;
+        CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
+                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream), ctx->wave, &nl));
+        ctx->launches += nl;
+        return 0;
+    }
+    CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
+                     d_out, launch_cfg(ctx, stream)));
     ctx->launches += 1;
     return 0;
 }
@@ -546,7 +603,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     std::string k(name);
     if (k == "integrator") { if (value != 0 && value != 1) return fail(ctx, "integrator must be 0 (v1) or 1 (v2)"); ctx->integrator = (int)value; }
     else if (k == "stats") ctx->stats = value != 0;
-    else if (k == "kernel") { if (value != 0 && value != 1) return fail(ctx, "kernel must be 0 (k_path) or 1 (simple megakernel)"); ctx->kernel = (int)value; }
+    else if (k == "kernel") { if (value < 0 || value > 2) return fail(ctx, "kernel must be 0 (k_path), 1 (simple megakernel) or 2 (wavefront)"); ctx->kernel = (int)value; }
     else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
     else return fail(ctx, "rt_set_option: unknown option '" + k + "'");
     return 0;

@@ -10,49 +10,11 @@
 // block at a time from a global counter (one atomic per warp, broadcast by shuffle), so rays of a
 // warp stay spatially coherent while load imbalance between hit/miss regions is evened out.
 #include "rt_kernels.h"
+#include "rt_kernel_common.cuh"
 
 namespace b200rt {
 
 namespace {
-
-constexpr int kThreads = 128;
-
-struct PixelWork { int i, j, out_index; bool active; };
-
-// Decode work item `w` (one 8x4 pixel block) for this lane.
-__device__ __forceinline__ PixelWork decode_work(const TileMap& tm, int w, int lane) {
-    int bx = tm.tile_w >> 3;
-    int per_tile = bx * (tm.tile_h >> 2);
-    int k = w / per_tile;                 // local tile number
-    int sub = w - k * per_tile;
-    int sy = sub / bx, sx = sub - sy * bx;
-    int tile = tm.first_tile + k * tm.tile_stride;
-    int ty = tile / tm.tiles_x, tx = tile - ty * tm.tiles_x;
-    int lx = (sx << 3) + (lane & 7), ly = (sy << 2) + (lane >> 3);
-    PixelWork p;
-    p.i = tx * tm.tile_w + lx;
-    p.j = ty * tm.tile_h + ly;
-    p.active = p.i < tm.width && p.j < tm.height;
-    p.out_index = tm.compact ? (k * tm.tile_h + ly) * tm.tile_w + lx : p.j * tm.width + p.i;
-    return p;
-}
-
-__device__ __forceinline__ int next_work(unsigned int* counter, int lane) {
-    unsigned int w = 0;
-    if (lane == 0) w = atomicAdd(counter, 1u);
-    return (int)__shfl_sync(0xffffffffu, w, 0);
-}
-
-__device__ __forceinline__ void flush_stats(unsigned long long* d_stats, unsigned long long rays,
-                                            const Counters& c) {
-    unsigned long long v[4] = {rays, c.segments, c.nodes, c.prims};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        unsigned long long x = v[q];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(d_stats + q, x);
-    }
-}
 
 template <bool TRI, bool STATS>
 __global__ void __launch_bounds__(kThreads)
@@ -285,21 +247,6 @@ __global__ void k_tonemap_u8(const float* __restrict__ accum, uint8_t* __restric
         x = fminf(fmaxf(x, 0.0f), 1.0f);
         out[k] = (uint8_t)__fmul_rn(x, 255.0f);
     }
-}
-
-template <typename K>
-int resident_grid(K kernel, int sm_count) {
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0);
-    if (per_sm < 1) per_sm = 1;
-    return sm_count * per_sm;
-}
-
-int work_items(const TileMap& tm) { return tm.n_local_tiles * (tm.tile_w >> 3) * (tm.tile_h >> 2); }
-
-int elementwise_grid(int64_t n) {
-    int64_t g = (n + 255) / 256;
-    return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));
 }
 
 }  // namespace

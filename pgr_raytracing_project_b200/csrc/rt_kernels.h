@@ -23,10 +23,25 @@ struct LaunchCfg {
     int sm_count;
     unsigned int* d_work_counter;            // zeroed by the launcher on `stream`
     unsigned long long* d_stats;             // [rays, segments, node_records, prim_tests] or nullptr
-    int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel
+    int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel, 2 = wavefront
     int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes
 };
 
+// Wavefront state in HBM (allocated by the context, float4 SoA).
+struct WaveBuffers {
+    float4* ray_o[2];        // origin | path slot (int bits); double-buffered by bounce parity
+    float4* ray_d[2];        // unit direction | 0
+    float4* hit;             // t | prim | slot | 0
+    float4* path_thr;        // throughput
+    float4* path_rad;        // radiance accumulated along the path
+    unsigned int* counters;  // [0..max_depth] queue sizes, then [0..max_depth] fetch cursors
+    int capacity;            // paths per wave
+};
+
+cudaError_t launch_wavefront(const SceneView& sc, bool is_tri, bool aov, const CameraBlock& cam, const TileMap& tm,
+                             int spp, int max_depth, int integrator, uint64_t seed, uint32_t sample_offset, int resolve,
+                             float* d_out, int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb,
+                             int* n_launches);
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
                                  int32_t* d_prim, float* d_t, const LaunchCfg& cfg);
 cudaError_t launch_trace_rays(const SceneView& sc, bool is_tri, const float* d_org, const float* d_dir, int64_t n,

@@ -1,0 +1,276 @@
+// rt_wavefront.cu -- wavefront form of the render hot path (kernel variant 2, sm_100a).
+//
+// A frame is processed in waves of paths (pixel task x sample).  Per wave:
+//   k_wf_generate     camera ray per path            -> ray queue 0 (compacted, warp-aggregated append)
+//   per bounce b:
+//     k_wf_trace      persistent threads; every lane pulls the next ray of queue b as soon as its own
+//                     traversal is finished (one atomic per refill, lanes ranked by ballot/popc), so the
+//                     warps stay full while the walk per ray is exactly intersect()'s -> hit records
+//     k_wf_shade      one thread per ray of queue b: emission / background, Russian roulette, scatter;
+//                     surviving paths are appended to queue b+1 (ballot/popc compaction)
+//   k_wf_accumulate   per pixel: add the wave's samples IN SAMPLE ORDER to the running sum (so the
+//                     frame is bit-identical to the megakernels'), resolve after the last wave
+// Ray / hit / path state live in HBM as float4 SoA (112 B per path in flight); at 2 M paths that is
+// ~0.25 GB per bounce of streaming traffic, i.e. tens of microseconds at B200 HBM bandwidth, in
+// exchange for full warps in both the traversal and the shading kernels.
+#include "rt_kernel_common.cuh"
+
+namespace b200rt {
+
+namespace {
+
+struct WaveArgs {
+    TileMap tm;
+    int task0, n_tasks_wave;      // pixel tasks [task0, task0 + n_tasks_wave) of the launch's enumeration
+    int sample0, batch;           // samples [sample0, sample0 + batch) of every pixel in this wave
+    int n_paths;                  // n_tasks_wave * batch
+    int spp, max_depth, integrator;
+    uint32_t k0, k1, sample_offset;
+    int resolve, last_wave;
+};
+
+__device__ __forceinline__ unsigned warp_append(unsigned int* counter, bool pred, int lane) {
+    unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0u) return 0u;
+    int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + (unsigned)__popc(m & ((1u << lane) - 1u));
+}
+
+template <bool STATS, bool AOV>
+__global__ void __launch_bounds__(256)
+k_wf_generate(const __grid_constant__ CameraBlock cam, const __grid_constant__ WaveArgs wa, WaveBuffers wb,
+              unsigned long long* d_stats) {
+    const int lane = threadIdx.x & 31;
+    const double inv_w = __ddiv_rn(1.0, (double)wa.tm.width), inv_h = __ddiv_rn(1.0, (double)wa.tm.height);
+    unsigned long long rays = 0;
+    const int n_round = (wa.n_paths + 31) & ~31;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n_round; slot += gridDim.x * blockDim.x) {
+        bool valid = slot < wa.n_paths;
+        Ray r;
+        if (valid) {
+            int task = wa.task0 + slot / wa.batch, sb = slot - (slot / wa.batch) * wa.batch;
+            PixelWork p = decode_work(wa.tm, task >> 5, task & 31);
+            valid = p.active;
+            if (valid) {
+                float jx = 0.5f, jy = 0.5f;
+                if (!AOV) {
+                    uint32_t pixel = (uint32_t)(p.j * wa.tm.width + p.i);
+                    uint4 ctl = philox4x32_10(pixel, wa.sample_offset + (uint32_t)(wa.sample0 + sb), 0u, 0u, wa.k0, wa.k1);
+                    jx = u01(ctl.x); jy = u01(ctl.y);
+                }
+                r = camera_ray(cam, p.i, p.j, jx, jy, inv_w, inv_h);
+                if (STATS) rays += 1;
+            }
+        }
+        unsigned q = warp_append(wb.counters, valid, lane);
+        if (valid) {
+            wb.ray_o[0][q] = make_float4(r.ox, r.oy, r.oz, __int_as_float(slot));
+            wb.ray_d[0][q] = make_float4(r.dx, r.dy, r.dz, 0.0f);
+            if (!AOV) {
+                wb.path_thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+                wb.path_rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+    }
+    if (STATS) { Counters c = {0, 0, 0}; flush_stats(d_stats, rays, c); }
+}
+
+template <bool TRI, bool STATS>
+__global__ void __launch_bounds__(kThreads)
+k_wf_trace(const __grid_constant__ SceneView sc, WaveBuffers wb, int bounce, int max_depth, int refill_below,
+           unsigned long long* d_stats) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float4* __restrict__ ray_o = wb.ray_o[bounce & 1];
+    const float4* __restrict__ ray_d = wb.ray_d[bounce & 1];
+    const unsigned count = wb.counters[bounce];
+    unsigned int* fetch = wb.counters + (max_depth + 1) + bounce;
+    int stack_code[kStackDepth];
+    float stack_tn[kStackDepth];
+    Trav tv;
+    tv.cur = kDone; tv.sp = 0; tv.h.t = kTMax; tv.h.prim = -1; tv.h.slot = -1;
+    Counters cnt = {0, 0, 0};
+    Ray r = make_ray(0.f, 0.f, 0.f, 0.f, 0.f, 1.f);
+    int q = -1;
+    bool pool_empty = false;
+    for (;;) {
+        bool idle = tv.cur == kDone;
+        if (idle && q >= 0) {                       // publish the finished ray's closest hit
+            wb.hit[q] = make_float4(tv.h.t, __int_as_float(tv.h.prim), __int_as_float(tv.h.slot), 0.0f);
+            q = -1;
+        }
+        unsigned need = __ballot_sync(0xffffffffu, idle);
+        if (need != 0u && !pool_empty) {
+            int n_need = __popc(need), leader = __ffs(need) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(fetch, (unsigned)n_need);
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (idle) {
+                unsigned idx = base + (unsigned)__popc(need & lt_mask);
+                if (idx < count) {
+                    q = (int)idx;
+                    float4 o = __ldg(ray_o + idx), d = __ldg(ray_d + idx);
+                    r = make_ray(o.x, o.y, o.z, d.x, d.y, d.z);
+                    trav_begin<STATS>(sc, r, tv, cnt);
+                }
+            }
+            if (base + (unsigned)n_need >= count) pool_empty = true;
+        }
+        unsigned act = __ballot_sync(0xffffffffu, tv.cur != kDone);
+        if (act == 0u) {
+            if (pool_empty && __ballot_sync(0xffffffffu, q >= 0) == 0u) break;
+            continue;                               // root misses waiting to be published / more to fetch
+        }
+        int min_active = pool_empty ? 1 : (__popc(act) * refill_below) >> 5;
+        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, cnt);
+    }
+    if (STATS) flush_stats(d_stats, 0, cnt);
+}
+
+template <bool TRI, bool STATS, bool AOV>
+__global__ void __launch_bounds__(256)
+k_wf_shade(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArgs wa, WaveBuffers wb, int bounce,
+           int32_t* __restrict__ d_prim, float* __restrict__ d_t, unsigned long long* d_stats) {
+    const int lane = threadIdx.x & 31;
+    const float4* __restrict__ ray_o = wb.ray_o[bounce & 1];
+    const float4* __restrict__ ray_d = wb.ray_d[bounce & 1];
+    float4* __restrict__ next_o = wb.ray_o[(bounce + 1) & 1];
+    float4* __restrict__ next_d = wb.ray_d[(bounce + 1) & 1];
+    const unsigned count = wb.counters[bounce];
+    const unsigned n_round = (count + 31u) & ~31u;
+    Counters cnt = {0, 0, 0};
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n_round; q += gridDim.x * blockDim.x) {
+        bool alive = false;
+        Ray r;
+        int slot = 0;
+        if (q < count) {
+            float4 o = ray_o[q], d = ray_d[q], hh = wb.hit[q];
+            slot = __float_as_int(o.w);
+            Hit h;
+            h.t = hh.x; h.prim = __float_as_int(hh.y); h.slot = __float_as_int(hh.z);
+            int task = wa.task0 + slot / wa.batch, sb = slot - (slot / wa.batch) * wa.batch;
+            PixelWork p = decode_work(wa.tm, task >> 5, task & 31);
+            if (STATS) cnt.segments += 1;
+            if (AOV) {
+                d_prim[p.out_index] = h.prim;
+                d_t[p.out_index] = h.prim >= 0 ? h.t : 0.0f;
+            } else {
+                float4 thr = wb.path_thr[slot], rad = wb.path_rad[slot];
+                if (h.prim < 0) {
+                    rad.x = __fmaf_rn(thr.x, sc.bg_r, rad.x); rad.y = __fmaf_rn(thr.y, sc.bg_g, rad.y); rad.z = __fmaf_rn(thr.z, sc.bg_b, rad.z);
+                } else {
+                    const float4* mp = sc.mats + 2 * (size_t)material_row<TRI>(sc, h);
+                    float4 m0 = __ldg(mp), m1 = __ldg(mp + 1);
+                    rad.x = __fmaf_rn(thr.x, m1.y, rad.x); rad.y = __fmaf_rn(thr.y, m1.z, rad.y); rad.z = __fmaf_rn(thr.z, m1.w, rad.z);
+                    if (bounce + 1 < wa.max_depth) {
+                        uint32_t pixel = (uint32_t)(p.j * wa.tm.width + p.i);
+                        uint32_t sample = wa.sample_offset + (uint32_t)(wa.sample0 + sb);
+                        uint4 ctl = philox4x32_10(pixel, sample, (uint32_t)bounce, 0u, wa.k0, wa.k1);
+                        r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
+                        alive = scatter<TRI>(sc, h, r, wa.integrator, bounce, wa.max_depth, ctl, m0, m1, pixel, sample,
+                                             wa.k0, wa.k1, thr.x, thr.y, thr.z);
+                        if (alive) wb.path_thr[slot] = thr;
+                    }
+                }
+                wb.path_rad[slot] = rad;
+            }
+        }
+        unsigned nq = warp_append(wb.counters + bounce + 1, alive, lane);
+        if (alive) {
+            next_o[nq] = make_float4(r.ox, r.oy, r.oz, __int_as_float(slot));
+            next_d[nq] = make_float4(r.dx, r.dy, r.dz, 0.0f);
+        }
+    }
+    if (STATS) flush_stats(d_stats, 0, cnt);
+}
+
+__global__ void __launch_bounds__(256)
+k_wf_accumulate(const __grid_constant__ WaveArgs wa, WaveBuffers wb, float* __restrict__ d_out) {
+    const float inv_spp = __fdiv_rn(1.0f, (float)wa.spp);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < wa.n_tasks_wave; k += gridDim.x * blockDim.x) {
+        int task = wa.task0 + k;
+        PixelWork p = decode_work(wa.tm, task >> 5, task & 31);
+        if (!p.active) continue;
+        float* o = d_out + 3 * (size_t)p.out_index;
+        float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+        if (wa.sample0 > 0) { sr = o[0]; sg = o[1]; sb = o[2]; }
+        for (int s = 0; s < wa.batch; ++s) {
+            float4 rad = wb.path_rad[(size_t)k * wa.batch + s];
+            sr = __fadd_rn(sr, rad.x); sg = __fadd_rn(sg, rad.y); sb = __fadd_rn(sb, rad.z);
+        }
+        if (wa.last_wave && wa.resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
+        else { o[0] = sr; o[1] = sg; o[2] = sb; }
+    }
+}
+
+int grid_for(int64_t n, int threads, int sm_count, int per_sm) {
+    int64_t g = (n + threads - 1) / threads;
+    int64_t cap = (int64_t)sm_count * per_sm;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <bool TRI, bool STATS, bool AOV>
+cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const TileMap& tm, int spp, int max_depth,
+                          int integrator, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out,
+                          int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb, int* n_launches) {
+    const int n_tasks = work_items(tm) * 32;
+    const int cap = wb.capacity;
+    const int chunk = n_tasks < cap ? n_tasks : (cap & ~31);
+    const int trace_grid = resident_grid(k_wf_trace<TRI, STATS>, cfg.sm_count);
+    cudaStream_t st = cfg.stream;
+    for (int task0 = 0; task0 < n_tasks; task0 += chunk) {
+        int nt = n_tasks - task0 < chunk ? n_tasks - task0 : chunk;
+        int batch_max = cap / nt;
+        if (batch_max < 1) batch_max = 1;
+        for (int s0 = 0; s0 < spp;) {
+            int batch = spp - s0 < batch_max ? spp - s0 : batch_max;
+            WaveArgs wa;
+            wa.tm = tm; wa.task0 = task0; wa.n_tasks_wave = nt; wa.sample0 = s0; wa.batch = batch;
+            wa.n_paths = nt * batch; wa.spp = spp; wa.max_depth = max_depth; wa.integrator = integrator;
+            wa.k0 = (uint32_t)seed; wa.k1 = (uint32_t)(seed >> 32); wa.sample_offset = sample_offset;
+            wa.resolve = resolve; wa.last_wave = s0 + batch >= spp;
+            cudaError_t e = cudaMemsetAsync(wb.counters, 0, sizeof(unsigned int) * 2 * (max_depth + 2), st);
+            if (e != cudaSuccess) return e;
+            k_wf_generate<STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(cam, wa, wb, cfg.d_stats);
+            *n_launches += 1;
+            int depth = AOV ? 1 : max_depth;
+            for (int b = 0; b < depth; ++b) {
+                k_wf_trace<TRI, STATS><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.d_stats);
+                k_wf_shade<TRI, STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(sc, wa, wb, b, d_prim, d_t,
+                                                                                                      cfg.d_stats);
+                *n_launches += 2;
+            }
+            if (!AOV) {
+                k_wf_accumulate<<<grid_for(nt, 256, cfg.sm_count, 8), 256, 0, st>>>(wa, wb, d_out);
+                *n_launches += 1;
+            }
+            s0 += batch;
+        }
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_wavefront(const SceneView& sc, bool is_tri, bool aov, const CameraBlock& cam, const TileMap& tm,
+                             int spp, int max_depth, int integrator, uint64_t seed, uint32_t sample_offset, int resolve,
+                             float* d_out, int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb,
+                             int* n_launches) {
+    if (work_items(tm) == 0) return cudaSuccess;
+    bool st = cfg.d_stats != nullptr;
+#define RUN(T, S, A) return run_wavefront<T, S, A>(sc, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, \
+                                                    d_out, d_prim, d_t, cfg, wb, n_launches)
+    if (aov) {
+        if (is_tri) { if (st) RUN(true, true, true); else RUN(true, false, true); }
+        else { if (st) RUN(false, true, true); else RUN(false, false, true); }
+    } else {
+        if (is_tri) { if (st) RUN(true, true, false); else RUN(true, false, false); }
+        else { if (st) RUN(false, true, false); else RUN(false, false, false); }
+    }
+#undef RUN
+}
+
+}  // namespace b200rt

@@ -20,10 +20,11 @@ pytestmark = pytest.mark.gpu
 REL_T = 1e-5
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["k_path", "simple"])
+@pytest.fixture(scope="module", params=[0, 1, 2], ids=["k_path", "simple", "wavefront"])
 def ctx(request):
     """Both tracing kernels must meet every bar: 0 = persistent path kernel with lane-level
-    continuation (default), 1 = simple one-pixel-per-thread megakernel."""
+    continuation, 1 = simple one-pixel-per-thread megakernel, 2 = wavefront (generate / trace / shade /
+    accumulate kernels with compacted ray queues)."""
     from pgr_raytracing_project_b200.context import RenderContext
     c = RenderContext(0)
     c.set_option("kernel", request.param)
