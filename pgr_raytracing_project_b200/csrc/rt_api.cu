@@ -49,7 +49,7 @@ struct rt_ctx {
     double fov = 45.0, aspect = 1.333;
 
     // options
-    int integrator = 0, stats = 0, kernel = 0, refill = 24;
+    int integrator = 0, stats = 0, kernel = 0, refill = 8, leaf_vote = 12;
 
     unsigned int* d_work_counter = nullptr;
     unsigned long long* d_stats = nullptr;   // rays, segments, node_records, prim_tests
@@ -214,6 +214,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream) {
     cfg.d_stats = c->stats ? c->d_stats : nullptr;
     cfg.variant = c->kernel;
     cfg.refill_below = c->refill;
+    cfg.leaf_vote = c->leaf_vote;
     return cfg;
 }
 
@@ -604,6 +605,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     if (k == "integrator") { if (value != 0 && value != 1) return fail(ctx, "integrator must be 0 (v1) or 1 (v2)"); ctx->integrator = (int)value; }
     else if (k == "stats") ctx->stats = value != 0;
     else if (k == "kernel") { if (value < 0 || value > 2) return fail(ctx, "kernel must be 0 (k_path), 1 (simple megakernel) or 2 (wavefront)"); ctx->kernel = (int)value; }
+    else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
     else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
     else return fail(ctx, "rt_set_option: unknown option '" + k + "'");
     return 0;
@@ -617,6 +619,7 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "stats") *value = ctx->stats;
     else if (k == "kernel") *value = ctx->kernel;
     else if (k == "refill") *value = ctx->refill;
+    else if (k == "leaf_vote") *value = ctx->leaf_vote;
     else if (k == "sm_count") *value = ctx->sm_count;
     else if (k == "bvh_depth") *value = ctx->bvh_depth;
     else if (k == "n_prims") *value = ctx->n;

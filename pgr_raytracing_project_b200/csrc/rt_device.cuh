@@ -249,11 +249,32 @@ __device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Tr
 }
 
 // Runs the warp's traversals until fewer than `min_active` lanes still have work (warp-uniform call).
+// Phase voting: in every iteration the warp executes EITHER one internal-node step (sibling pair
+// fetch + two slab tests) OR one leaf step (its <= 4 primitives), whichever the vote picks, and only
+// the lanes currently in that phase run it; the others wait for their phase's turn.  Lanes thereby
+// regroup by phase (software re-convergence) instead of idling through each other's inner loops --
+// the per-ray visiting order, and with it every counter, stays exactly intersect()'s.
+// leaf_vote: the leaf phase runs when at least that many lanes hold a leaf (or no lane holds an
+// internal node).
 template <bool TRI, bool STATS>
 __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav& tv, int* stack_code,
-                                         float* stack_tn, int min_active, Counters& cnt) {
+                                         float* stack_tn, int min_active, int leaf_vote, Counters& cnt) {
     for (;;) {
-        while (tv.cur >= 0) {                                   // internal nodes
+        const bool is_int = tv.cur >= 0, is_leaf = tv.cur < kDone;
+        const int n_int = __popc(__ballot_sync(0xffffffffu, is_int));
+        const int n_leaf = __popc(__ballot_sync(0xffffffffu, is_leaf));
+        if (n_int + n_leaf < min_active) break;
+        if (n_int == 0 || n_leaf >= leaf_vote) {
+            if (is_leaf) {
+                int code = ~tv.cur;
+                int first = code >> 3, count = code & 7;
+                for (int k = 0; k < count; ++k) {
+                    if (STATS) cnt.prims += 1;
+                    test_prim<TRI>(sc, first + k, r, tv.h);
+                }
+                trav_pop(tv, stack_code, stack_tn);
+            }
+        } else if (is_int) {
             const float4* p = sc.nodes + 2 * (size_t)tv.cur;
             float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
             if (STATS) cnt.nodes += 2;
@@ -270,16 +291,6 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
             else if (hr) tv.cur = rc;
             else trav_pop(tv, stack_code, stack_tn);
         }
-        if (tv.cur < kDone) {                                   // one leaf
-            int code = ~tv.cur;
-            int first = code >> 3, count = code & 7;
-            for (int k = 0; k < count; ++k) {
-                if (STATS) cnt.prims += 1;
-                test_prim<TRI>(sc, first + k, r, tv.h);
-            }
-            trav_pop(tv, stack_code, stack_tn);
-        }
-        if (__popc(__ballot_sync(0xffffffffu, tv.cur != kDone)) < min_active) break;
     }
 }
 

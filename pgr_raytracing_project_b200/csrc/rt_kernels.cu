@@ -106,7 +106,7 @@ template <bool TRI, bool STATS, bool AOV>
 __global__ void __launch_bounds__(kThreads)
 k_path(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock cam,
        const __grid_constant__ TileMap tm, int n_tasks, int spp, int max_depth, int integrator, uint32_t k0,
-       uint32_t k1, uint32_t sample_offset, int resolve, int refill_below, float* __restrict__ d_out,
+       uint32_t k1, uint32_t sample_offset, int resolve, int refill_below, int leaf_vote, float* __restrict__ d_out,
        int32_t* __restrict__ d_prim, float* __restrict__ d_t, unsigned int* counter, unsigned long long* d_stats) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -206,7 +206,7 @@ k_path(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
         if (act == 0u) break;                      // every lane idle and the pool is empty
         // leave the loop again once a quarter (32 - refill_below in 32) of the lanes that entered are done
         int min_active = (__popc(act) * refill_below) >> 5;
-        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, cnt);
+        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, leaf_vote, cnt);
         if (phase == PH_TRAV && tv.cur == kDone) phase = PH_SHADE;
     }
     if (STATS) flush_stats(d_stats, rays, cnt);
@@ -263,7 +263,7 @@ cudaError_t launch_path(const SceneView& sc, const CameraBlock& cam, const TileM
     if (grid > need) grid = need;
     k_path<TRI, STATS, AOV><<<grid, kThreads, 0, cfg.stream>>>(
         sc, cam, tm, n_work * 32, spp, max_depth, integrator, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset,
-        resolve, cfg.refill_below, d_out, d_prim, d_t, cfg.d_work_counter, cfg.d_stats);
+        resolve, cfg.refill_below, cfg.leaf_vote, d_out, d_prim, d_t, cfg.d_work_counter, cfg.d_stats);
     return cudaGetLastError();
 }
 

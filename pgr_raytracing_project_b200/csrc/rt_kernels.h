@@ -25,6 +25,7 @@ struct LaunchCfg {
     unsigned long long* d_stats;             // [rays, segments, node_records, prim_tests] or nullptr
     int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel, 2 = wavefront
     int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes
+    int leaf_vote;                           // phase voting: leaf step when >= this many lanes hold a leaf
 };
 
 // Wavefront state in HBM (allocated by the context, float4 SoA).

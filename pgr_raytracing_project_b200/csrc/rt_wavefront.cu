@@ -41,7 +41,7 @@ __device__ __forceinline__ unsigned warp_append(unsigned int* counter, bool pred
 
 template <bool STATS, bool AOV>
 __global__ void __launch_bounds__(256)
-k_wf_generate(const __grid_constant__ CameraBlock cam, const __grid_constant__ WaveArgs wa, WaveBuffers wb,
+k_wf_generate(const __grid_constant__ CameraBlock cam, const __grid_constant__ WaveArgs wa, const __grid_constant__ WaveBuffers wb,
               unsigned long long* d_stats) {
     const int lane = threadIdx.x & 31;
     const double inv_w = __ddiv_rn(1.0, (double)wa.tm.width), inv_h = __ddiv_rn(1.0, (double)wa.tm.height);
@@ -80,8 +80,8 @@ k_wf_generate(const __grid_constant__ CameraBlock cam, const __grid_constant__ W
 
 template <bool TRI, bool STATS>
 __global__ void __launch_bounds__(kThreads)
-k_wf_trace(const __grid_constant__ SceneView sc, WaveBuffers wb, int bounce, int max_depth, int refill_below,
-           unsigned long long* d_stats) {
+k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuffers wb, int bounce, int max_depth, int refill_below,
+           int leaf_vote, unsigned long long* d_stats) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float4* __restrict__ ray_o = wb.ray_o[bounce & 1];
@@ -125,14 +125,14 @@ k_wf_trace(const __grid_constant__ SceneView sc, WaveBuffers wb, int bounce, int
             continue;                               // root misses waiting to be published / more to fetch
         }
         int min_active = pool_empty ? 1 : (__popc(act) * refill_below) >> 5;
-        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, cnt);
+        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, leaf_vote, cnt);
     }
     if (STATS) flush_stats(d_stats, 0, cnt);
 }
 
 template <bool TRI, bool STATS, bool AOV>
 __global__ void __launch_bounds__(256)
-k_wf_shade(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArgs wa, WaveBuffers wb, int bounce,
+k_wf_shade(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArgs wa, const __grid_constant__ WaveBuffers wb, int bounce,
            int32_t* __restrict__ d_prim, float* __restrict__ d_t, unsigned long long* d_stats) {
     const int lane = threadIdx.x & 31;
     const float4* __restrict__ ray_o = wb.ray_o[bounce & 1];
@@ -188,7 +188,7 @@ k_wf_shade(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArg
 }
 
 __global__ void __launch_bounds__(256)
-k_wf_accumulate(const __grid_constant__ WaveArgs wa, WaveBuffers wb, float* __restrict__ d_out) {
+k_wf_accumulate(const __grid_constant__ WaveArgs wa, const __grid_constant__ WaveBuffers wb, float* __restrict__ d_out) {
     const float inv_spp = __fdiv_rn(1.0f, (float)wa.spp);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < wa.n_tasks_wave; k += gridDim.x * blockDim.x) {
         int task = wa.task0 + k;
@@ -238,7 +238,7 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
             *n_launches += 1;
             int depth = AOV ? 1 : max_depth;
             for (int b = 0; b < depth; ++b) {
-                k_wf_trace<TRI, STATS><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.d_stats);
+                k_wf_trace<TRI, STATS><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
                 k_wf_shade<TRI, STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(sc, wa, wb, b, d_prim, d_t,
                                                                                                       cfg.d_stats);
                 *n_launches += 2;
