@@ -152,10 +152,12 @@ int rt_tonemap_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
 
 /* ---- options and counters.  Options: "integrator" 0 = v1 semantics (default; the generation
  * that runs: RR `depth<3 || rand<0.8` unweighted, metal chosen with probability metallic),
- * 1 = v2 semantics (raytracer_core.cpp:317-347); "stats" 0/1; "kernel" 0 = persistent path
- * kernel with lane-level continuation (default), 1 = simple one-pixel-per-thread megakernel (same
- * results, kept for A/B profiling); "refill" 1..32 = lane count below which a warp of kernel 0
- * leaves the traversal loop to shade / refill (default 24). */
+ * 1 = v2 semantics (raytracer_core.cpp:317-347); "stats" 0/1; "kernel" -1 = auto (default: picks by
+ * scene size and max_depth), 0 = persistent path kernel with lane-level continuation, 1 = simple
+ * one-pixel-per-thread megakernel, 2 = wavefront (generate / trace / shade / accumulate kernels over
+ * compacted ray queues) -- all three give bit-identical results; "refill" 1..32 = share (in 32nds)
+ * of a warp's traversing lanes below which it leaves the traversal loop to shade / refill (default
+ * 8); "leaf_vote" 1..32 = lanes holding a leaf at which the warp runs the leaf step (default 8). */
 int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);
 int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value);
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);   /* synchronises the device */

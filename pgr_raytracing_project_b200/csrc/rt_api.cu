@@ -49,7 +49,7 @@ struct rt_ctx {
     double fov = 45.0, aspect = 1.333;
 
     // options
-    int integrator = 0, stats = 0, kernel = 0, refill = 8, leaf_vote = 12;
+    int integrator = 0, stats = 0, kernel = -1, refill = 8, leaf_vote = 8;
 
     unsigned int* d_work_counter = nullptr;
     unsigned long long* d_stats = nullptr;   // rays, segments, node_records, prim_tests
@@ -206,13 +206,22 @@ SceneView scene_view(const rt_ctx* c) {
     return v;
 }
 
-LaunchCfg launch_cfg(rt_ctx* c, void* stream) {
+// Kernel choice when option "kernel" is -1 (auto), from B200 measurements (DESIGN.md "Kernel choice"):
+// tiny scenes are shading-bound and favour the lock-step megakernel; multi-bounce paths favour the
+// wavefront queues; single-segment (primary-ray) work favours the persistent path kernel.
+int pick_kernel(const rt_ctx* c, int max_depth) {
+    if (c->kernel >= 0) return c->kernel;
+    if (c->n <= 64) return 1;
+    return max_depth >= 2 ? 2 : 0;
+}
+
+LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1) {
     LaunchCfg cfg;
     cfg.stream = (cudaStream_t)stream;
     cfg.sm_count = c->sm_count;
     cfg.d_work_counter = c->d_work_counter;
     cfg.d_stats = c->stats ? c->d_stats : nullptr;
-    cfg.variant = c->kernel;
+    cfg.variant = pick_kernel(c, max_depth);
     cfg.refill_below = c->refill;
     cfg.leaf_vote = c->leaf_vote;
     return cfg;
@@ -417,7 +426,7 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
     ctx->aspect = (double)width / height;            // RayTracer::render, old/raytracer_core copy.cpp:259
     CameraBlock cam = camera_block(ctx, ctx->aspect);
     TileMap tm = full_frame_map(width, height);
-    if (ctx->kernel == 2) {
+    if (pick_kernel(ctx, 1) == 2) {
         if (int rc = ensure_wave(ctx, task_count(tm), 1, 1)) return rc;
         int nl = 0;
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, true, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t,
@@ -488,16 +497,16 @@ int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, 
     tm.first_tile = first_tile; tm.tile_stride = tile_stride;
     tm.n_local_tiles = first_tile < tm.n_tiles ? (tm.n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
     tm.compact = 1;
-    if (ctx->kernel == 2 && tm.n_local_tiles) {
+    if (pick_kernel(ctx, max_depth) == 2 && tm.n_local_tiles) {
         if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
         int nl = 0;
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
-                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream), ctx->wave, &nl));
+                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream, max_depth), ctx->wave, &nl));
         ctx->launches += nl;
         return 0;
     }
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
-                     d_out, launch_cfg(ctx, stream)));
+                     d_out, launch_cfg(ctx, stream, max_depth)));
     if (tm.n_local_tiles) ctx->launches += 1;
     return 0;
 }
@@ -512,16 +521,16 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
     ctx->aspect = (double)width / height;
     CameraBlock cam = camera_block(ctx, ctx->aspect);
     TileMap tm = full_frame_map(width, height);
-    if (ctx->kernel == 2) {
+    if (pick_kernel(ctx, max_depth) == 2) {
         if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
         int nl = 0;
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
-                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream), ctx->wave, &nl));
+                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream, max_depth), ctx->wave, &nl));
         ctx->launches += nl;
         return 0;
     }
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
-                     d_out, launch_cfg(ctx, stream)));
+                     d_out, launch_cfg(ctx, stream, max_depth)));
     ctx->launches += 1;
     return 0;
 }
@@ -604,7 +613,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     std::string k(name);
     if (k == "integrator") { if (value != 0 && value != 1) return fail(ctx, "integrator must be 0 (v1) or 1 (v2)"); ctx->integrator = (int)value; }
     else if (k == "stats") ctx->stats = value != 0;
-    else if (k == "kernel") { if (value < 0 || value > 2) return fail(ctx, "kernel must be 0 (k_path), 1 (simple megakernel) or 2 (wavefront)"); ctx->kernel = (int)value; }
+    else if (k == "kernel") { if (value < -1 || value > 2) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel) or 2 (wavefront)"); ctx->kernel = (int)value; }
     else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
     else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
     else return fail(ctx, "rt_set_option: unknown option '" + k + "'");
