@@ -62,7 +62,7 @@ def profile_traffic():
     """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
     p = os.path.join(ROOT, "profiles", "latest_traffic.json")
     try:
-        return json.load(open(p)).get("k_render_dram_bytes_per_launch")
+        return json.load(open(p)).get("dram_bytes_per_launch")
     except Exception:  # noqa: BLE001
         return None
 
@@ -326,6 +326,10 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     peak, peak_src = measured_peaks()
+    kernel_name = {0: "k_path<TRI> (persistent path kernel: raygen + BVH traversal + shade + resolve, lane-level continuation)",
+                   1: "k_render<TRI> (one-pixel-per-thread megakernel: raygen + BVH traversal + shade + resolve)",
+                   2: "k_wf_trace<TRI> (wavefront: generate / trace / shade / accumulate; trace dominates)"}.get(
+                       ctx.get_option("kernel_used"), "?")
     achieved = rays_per_launch * bytes_per_ray / (kernel_ms / 1e3) / 1e9
     # warm-L2 figure for context (no flush between launches)
     torch.cuda.synchronize()
@@ -391,7 +395,7 @@ def main():
             "gpu_launches": int(n_launch.item()),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": profile_traffic(), "kernel": "k_render<TRI> (megakernel: raygen + BVH traversal + shade + resolve)",
+                "traffic": profile_traffic(), "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "kernel_ms_warm_l2": warm_ms, "peak_source": peak_src,
                 "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                 "rays_per_launch": rays_per_launch,

@@ -50,6 +50,7 @@ struct rt_ctx {
 
     // options
     int integrator = 0, stats = 0, kernel = -1, refill = 8, leaf_vote = 8;
+    int kernel_used = -1;                    // variant picked by the most recent tracing launch
 
     unsigned int* d_work_counter = nullptr;
     unsigned long long* d_stats = nullptr;   // rays, segments, node_records, prim_tests
@@ -222,6 +223,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1) {
     cfg.d_work_counter = c->d_work_counter;
     cfg.d_stats = c->stats ? c->d_stats : nullptr;
     cfg.variant = pick_kernel(c, max_depth);
+    c->kernel_used = cfg.variant;
     cfg.refill_below = c->refill;
     cfg.leaf_vote = c->leaf_vote;
     return cfg;
@@ -627,6 +629,7 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     if (k == "integrator") *value = ctx->integrator;
     else if (k == "stats") *value = ctx->stats;
     else if (k == "kernel") *value = ctx->kernel;
+    else if (k == "kernel_used") *value = ctx->kernel_used;
     else if (k == "refill") *value = ctx->refill;
     else if (k == "leaf_vote") *value = ctx->leaf_vote;
     else if (k == "sm_count") *value = ctx->sm_count;
