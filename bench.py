@@ -271,17 +271,29 @@ def main():
         return renderer.render(W, H, spp_total, MAX_DEPTH, RENDER_SEED, k * spp_total)
 
     # exact work counters of the timed steps (instrumented kernel variant, outside the timed region)
-    ctx.set_option("stats", 1)
-    ctx.reset_stats()
-    for k in range(args.steps):
-        first = k * spp_total + rank * SPP_PER_GPU
-        ctx.render_sum(W, H, SPP_PER_GPU, MAX_DEPTH, RENDER_SEED, first, out=renderer._buf("part", (H, W, 3)))
-    st = ctx.stats()
-    ctx.set_option("stats", 0)
+    # Per-ray counters are SURVEY.md 8(d)'s definition (what the oracle counts: every node record and
+    # triangle one ray's own near-first walk fetches), taken from the instrumented per-ray kernel (option
+    # kernel=0) on exactly the timed rays.  The packet kernel's own counters (what a 32-ray packet really
+    # fetched, once) are reported next to them as `fetched_*`.
+    def count(kernel):
+        ctx.set_option("kernel", kernel)
+        ctx.set_option("stats", 1)
+        ctx.reset_stats()
+        for k in range(args.steps):
+            first = k * spp_total + rank * SPP_PER_GPU
+            ctx.render_sum(W, H, SPP_PER_GPU, MAX_DEPTH, RENDER_SEED, first, out=renderer._buf("part", (H, W, 3)))
+        st = ctx.stats()
+        ctx.set_option("stats", 0)
+        ctx.set_option("kernel", -1)
+        return st
+
+    st = count(0)
     rays_per_launch = st["rays"] / args.steps
     nodes_per_ray = st["node_records"] / st["rays"]
     tris_per_ray = st["prim_tests"] / st["rays"]
     bytes_per_ray = BYTES_NODE * nodes_per_ray + BYTES_TRI * tris_per_ray + BYTES_OUT
+    stp = count(-1)
+    fetched_bytes_per_ray = (BYTES_NODE * stp["node_records"] + BYTES_TRI * stp["prim_tests"]) / stp["rays"] + BYTES_OUT
 
     for k in range(args.warmup):
         flush.zero_()
@@ -328,7 +340,9 @@ def main():
     peak, peak_src = measured_peaks()
     kernel_name = {0: "k_path<TRI> (persistent path kernel: raygen + BVH traversal + shade + resolve, lane-level continuation)",
                    1: "k_render<TRI> (one-pixel-per-thread megakernel: raygen + BVH traversal + shade + resolve)",
-                   2: "k_wf_trace<TRI> (wavefront: generate / trace / shade / accumulate; trace dominates)"}.get(
+                   2: "k_wf_trace<TRI> (wavefront: generate / trace / shade / accumulate; trace dominates)",
+                   3: "k_packet<TRI> (camera-ray packets: raygen + shared-stack BVH traversal + shade + resolve; "
+                      "kernel_ms includes its per-frame k_cam_tris table pass)"}.get(
                        ctx.get_option("kernel_used"), "?")
     achieved = rays_per_launch * bytes_per_ray / (kernel_ms / 1e3) / 1e9
     # warm-L2 figure for context (no flush between launches)
@@ -398,10 +412,13 @@ def main():
                 "traffic": profile_traffic(), "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "kernel_ms_warm_l2": warm_ms, "peak_source": peak_src,
                 "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
-                "rays_per_launch": rays_per_launch,
-                "note": "algorithmic bytes: every 32-B node record and 48-B triangle fetched counts, no credit for cache "
-                        "hits; the working set is L2-resident, so this is a traversal-rate figure rated against HBM "
-                        "copy bandwidth",
+                "rays_per_launch": rays_per_launch, "fetched_bytes_per_ray": fetched_bytes_per_ray,
+                "achieved_fetched": rays_per_launch * fetched_bytes_per_ray / (kernel_ms / 1e3) / 1e9,
+                "note": "algorithmic bytes (SURVEY 8(d)): every 32-B node record and 48-B triangle that ONE RAY's own "
+                        "near-first walk fetches, no credit for cache hits or for sharing; the working set (64 MB) is "
+                        "L2-resident and the packet kernel fetches each record once per 32-ray packet "
+                        "(fetched_bytes_per_ray, achieved_fetched), so `achieved` is a traversal-rate figure rated "
+                        "against HBM copy bandwidth and may exceed it; the limiter is instruction issue (profiles/)",
             },
         }
         if world == 1 and not args.no_cpu_baseline:

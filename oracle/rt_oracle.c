@@ -38,7 +38,7 @@
  *   pixel loop, mean, sqrt, clamp . cpp_raytracer/raytracer_core.cpp:381-409
  * Deliberate, documented departures (DESIGN.md "Arithmetic contract"): Philox4x32-10
  * counter RNG instead of PCG32/mt19937; closest-hit ties go to the lower primitive index;
- * triangle primitive (Moller-Trumbore) added; node boxes padded by 2^-16 * scene scale.
+ * triangle primitive (Moller-Trumbore in triple-product form, see test_tri) added; node boxes padded by 2^-16 * scene scale.
  *
  * Arithmetic contract (shared with the CUDA kernels, written independently there): IEEE
  * float32, no implicit contraction (compile with -ffp-contract=off, no -ffast-math), explicit
@@ -86,6 +86,15 @@ static inline v3 cross3(v3 a, v3 b) {
     r.x = fmaf(a.y, b.z, -(a.z * b.y));
     r.y = fmaf(a.z, b.x, -(a.x * b.z));
     r.z = fmaf(a.x, b.y, -(a.y * b.x));
+    return r;
+}
+/* exactly antisymmetric cross product (both products rounded, then subtracted): cross_as(a,b) ==
+ * -cross_as(b,a) bit for bit, which keeps the shared edge of two triangles of a fan watertight */
+static inline v3 cross_as(v3 a, v3 b) {
+    v3 r;
+    r.x = a.y * b.z - a.z * b.y;
+    r.y = a.z * b.x - a.x * b.z;
+    r.z = a.x * b.y - a.y * b.x;
     return r;
 }
 static inline v3 sub3(v3 a, v3 b) { v3 r = {a.x - b.x, a.y - b.y, a.z - b.z}; return r; }
@@ -356,21 +365,32 @@ static inline void test_sphere(const scene_t* s, int32_t prim, const ray_t* r, f
     consider(h, t, prim, tmin);
 }
 
+/* Ray/triangle test (an extension: the reference has no triangle primitive).  Moller-Trumbore
+ * written as scalar triple products of the ray direction d with three vectors that depend only on
+ * the triangle and the ray ORIGIN:   det = d.(e2 x e1),  u*det = d.(e2 x s),  v*det = d.(s x e1),
+ * t*det = e2.(s x e1),  s = o - v0.  The inside test is division-free (compare against det after
+ * making det positive; negation is exact), the hit distance is one IEEE division.  The CUDA
+ * kernels evaluate the same expression tree; for camera rays (one shared origin) they read
+ * (e2 x e1, e2 x s, s x e1, e2.(s x e1)) from a per-frame table computed with these very
+ * operations, so both routes give the same bits.  The cross products are the exactly antisymmetric
+ * cross_as(): for two triangles that share v0 and an edge vector (the two halves of a quad) u*det of
+ * one is then exactly -v*det of the other, so a ray through the shared edge is accepted by at least
+ * one of them (no cracks along quad diagonals). */
 static inline void test_tri(const scene_t* s, int32_t prim, const ray_t* r, float tmin, hit_t* h) {
     const float* p = s->v0e + 9 * (int64_t)prim;
     v3 v0 = {p[0], p[1], p[2]}, e1 = {p[3], p[4], p[5]}, e2 = {p[6], p[7], p[8]};
-    v3 pv = cross3(r->d, e2);
-    float det = dot3(e1, pv);
-    if (det == 0.0f) return;
-    float inv = 1.0f / det;
     v3 sv = sub3(r->o, v0);
-    float u = dot3(sv, pv) * inv;
-    if (!(u >= 0.0f && u <= 1.0f)) return;
-    v3 qv = cross3(sv, e1);
-    float v = dot3(r->d, qv) * inv;
-    if (!(v >= 0.0f && u + v <= 1.0f)) return;
-    float t = dot3(e2, qv) * inv;
-    consider(h, t, prim, tmin);
+    v3 nn = cross_as(e2, e1);
+    float det = dot3(r->d, nn);
+    if (det == 0.0f) return;
+    v3 av = cross_as(e2, sv);
+    float un = dot3(r->d, av);
+    v3 bv = cross_as(sv, e1);
+    float vn = dot3(r->d, bv);
+    float c = dot3(e2, bv);
+    if (det < 0.0f) { det = -det; un = -un; vn = -vn; c = -c; }
+    if (!(un >= 0.0f && vn >= 0.0f && un + vn <= det)) return;
+    consider(h, c / det, prim, tmin);
 }
 
 static inline void test_prim(const scene_t* s, int32_t prim, const ray_t* r, float tmin, hit_t* h) {

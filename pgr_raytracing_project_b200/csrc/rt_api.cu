@@ -40,6 +40,7 @@ struct rt_ctx {
     // device copies
     float4* d_nodes = nullptr;
     float4* d_prims = nullptr;
+    float4* d_cam_prims = nullptr;           // triangles: per-frame camera-relative records (k_cam_tris)
     int* d_slot_prim = nullptr;
     float4* d_mats = nullptr;
     bool device_valid = false;
@@ -88,8 +89,8 @@ int cuda_fail(rt_ctx* c, const char* what, cudaError_t e) {
     } while (0)
 
 void free_device_scene(rt_ctx* c) {
-    cudaFree(c->d_nodes); cudaFree(c->d_prims); cudaFree(c->d_slot_prim); cudaFree(c->d_mats);
-    c->d_nodes = c->d_prims = c->d_mats = nullptr; c->d_slot_prim = nullptr;
+    cudaFree(c->d_nodes); cudaFree(c->d_prims); cudaFree(c->d_cam_prims); cudaFree(c->d_slot_prim); cudaFree(c->d_mats);
+    c->d_nodes = c->d_prims = c->d_cam_prims = c->d_mats = nullptr; c->d_slot_prim = nullptr;
     c->device_valid = false;
 }
 
@@ -174,6 +175,7 @@ int ensure_device(rt_ctx* ctx) {
         }
         CK(cudaMalloc(&ctx->d_prims, prims.size() * sizeof(float4)));
         CK(cudaMemcpy(ctx->d_prims, prims.data(), prims.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        if (ctx->is_tri) CK(cudaMalloc(&ctx->d_cam_prims, prims.size() * sizeof(float4)));
         CK(cudaMalloc(&ctx->d_slot_prim, (size_t)n * sizeof(int)));
         CK(cudaMemcpy(ctx->d_slot_prim, ctx->prim_index.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&ctx->d_nodes, (size_t)n_nodes * sizeof(rt_bvh_node)));
@@ -209,11 +211,11 @@ SceneView scene_view(const rt_ctx* c) {
 
 // Kernel choice when option "kernel" is -1 (auto), from B200 measurements (DESIGN.md "Kernel choice"):
 // tiny scenes are shading-bound and favour the lock-step megakernel; multi-bounce paths favour the
-// wavefront queues; single-segment (primary-ray) work favours the persistent path kernel.
+// wavefront queues; single-segment (camera-ray) work favours the packet kernel.
 int pick_kernel(const rt_ctx* c, int max_depth) {
-    if (c->kernel >= 0) return c->kernel;
+    if (c->kernel >= 0) return (c->kernel == 3 && max_depth != 1) ? 0 : c->kernel;
     if (c->n <= 64) return 1;
-    return max_depth >= 2 ? 2 : 0;
+    return max_depth >= 2 ? 2 : 3;
 }
 
 LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1) {
@@ -224,6 +226,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1) {
     cfg.d_stats = c->stats ? c->d_stats : nullptr;
     cfg.variant = pick_kernel(c, max_depth);
     c->kernel_used = cfg.variant;
+    cfg.d_cam_prims = c->d_cam_prims;
     cfg.refill_below = c->refill;
     cfg.leaf_vote = c->leaf_vote;
     return cfg;
@@ -437,7 +440,7 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
         return 0;
     }
     CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, tm, d_prim, d_t, launch_cfg(ctx, stream)));
-    ctx->launches += 1;
+    ctx->launches += (ctx->kernel_used == 3 && ctx->is_tri) ? 2 : 1;      // k_cam_tris + k_packet
     return 0;
 }
 
@@ -509,7 +512,7 @@ int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, 
     }
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, launch_cfg(ctx, stream, max_depth)));
-    if (tm.n_local_tiles) ctx->launches += 1;
+    if (tm.n_local_tiles) ctx->launches += (ctx->kernel_used == 3 && ctx->is_tri) ? 2 : 1;
     return 0;
 }
 
@@ -533,7 +536,7 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
     }
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, launch_cfg(ctx, stream, max_depth)));
-    ctx->launches += 1;
+    ctx->launches += (ctx->kernel_used == 3 && ctx->is_tri) ? 2 : 1;
     return 0;
 }
 
@@ -615,7 +618,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     std::string k(name);
     if (k == "integrator") { if (value != 0 && value != 1) return fail(ctx, "integrator must be 0 (v1) or 1 (v2)"); ctx->integrator = (int)value; }
     else if (k == "stats") ctx->stats = value != 0;
-    else if (k == "kernel") { if (value < -1 || value > 2) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel) or 2 (wavefront)"); ctx->kernel = (int)value; }
+    else if (k == "kernel") { if (value < -1 || value > 3) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront) or 3 (camera-ray packets)"); ctx->kernel = (int)value; }
     else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
     else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
     else return fail(ctx, "rt_set_option: unknown option '" + k + "'");

@@ -56,6 +56,14 @@ __device__ __forceinline__ void cross3(float ax, float ay, float az, float bx, f
     ry = __fmaf_rn(az, bx, -__fmul_rn(ax, bz));
     rz = __fmaf_rn(ax, by, -__fmul_rn(ay, bx));
 }
+// exactly antisymmetric cross product (both products rounded, then subtracted): used by the triangle
+// test so that the shared edge of the two halves of a quad is watertight (oracle: cross_as)
+__device__ __forceinline__ void cross_as(float ax, float ay, float az, float bx, float by, float bz,
+                                         float& rx, float& ry, float& rz) {
+    rx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+    ry = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+    rz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+}
 __device__ __forceinline__ void normalize3(float& x, float& y, float& z) {   // raytracer_core.h:91-94
     float len = __fsqrt_rn(dot3(x, y, z, x, y, z));
     if (len > 0.0f) {
@@ -124,25 +132,51 @@ __device__ __forceinline__ void consider(Hit& h, float t, int prim, int slot) {
     if (t < h.t || h.prim < 0 || prim < h.prim) { h.t = t; h.prim = prim; h.slot = slot; }
 }
 
+// Ray/triangle test: Moller-Trumbore as scalar triple products of the direction d with vectors that
+// depend only on the triangle and the ray origin (s = o - v0):
+//   det = d.(e2 x e1)   u*det = d.(e2 x s)   v*det = d.(s x e1)   t*det = e2.(s x e1)
+// inside test division-free (against det made positive; negation is exact), distance = one IEEE
+// division.  tri_finish() is shared by the general route (vectors computed per ray) and the camera
+// route (vectors read from the per-frame table written by cam_tri_record for the shared origin), so
+// both give the same bits -- and so does oracle/rt_oracle.c test_tri.
+__device__ __forceinline__ void tri_finish(Hit& h, float dx, float dy, float dz, float nx, float ny, float nz,
+                                           float ax, float ay, float az, float bx, float by, float bz, float c,
+                                           int prim, int slot) {
+    float det = dot3(dx, dy, dz, nx, ny, nz);
+    if (det == 0.0f) return;
+    float un = dot3(dx, dy, dz, ax, ay, az);
+    float vn = dot3(dx, dy, dz, bx, by, bz);
+    if (det < 0.0f) { det = -det; un = -un; vn = -vn; c = -c; }
+    if (!(un >= 0.0f && vn >= 0.0f && __fadd_rn(un, vn) <= det)) return;
+    consider(h, __fdiv_rn(c, det), prim, slot);
+}
+
+// (e2 x e1 | e2.(s x e1)), (e2 x s | prim), (s x e1 | material) for origin (ox,oy,oz)
+__device__ __forceinline__ void cam_tri_record(float4 v0, float4 e1, float4 e2, float ox, float oy, float oz,
+                                               float4& r0, float4& r1, float4& r2) {
+    float sx = __fsub_rn(ox, v0.x), sy = __fsub_rn(oy, v0.y), sz = __fsub_rn(oz, v0.z);
+    cross_as(e2.x, e2.y, e2.z, e1.x, e1.y, e1.z, r0.x, r0.y, r0.z);
+    cross_as(e2.x, e2.y, e2.z, sx, sy, sz, r1.x, r1.y, r1.z);
+    cross_as(sx, sy, sz, e1.x, e1.y, e1.z, r2.x, r2.y, r2.z);
+    r0.w = dot3(e2.x, e2.y, e2.z, r2.x, r2.y, r2.z);
+    r1.w = v0.w; r2.w = e1.w;
+}
+
+// camera route: record `slot` of the per-frame table
+__device__ __forceinline__ void test_cam_tri(const float4* __restrict__ cam_prims, int slot, const Ray& r, Hit& h) {
+    const float4* p = cam_prims + 3 * (size_t)slot;
+    float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
+    tri_finish(h, r.dx, r.dy, r.dz, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r0.w, __float_as_int(r1.w), slot);
+}
+
 template <bool TRI>
 __device__ __forceinline__ void test_prim(const SceneView& sc, int slot, const Ray& r, Hit& h) {
     if (TRI) {
         const float4* p = sc.prims + 3 * (size_t)slot;
         float4 v0 = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
-        float px, py, pz;
-        cross3(r.dx, r.dy, r.dz, e2.x, e2.y, e2.z, px, py, pz);
-        float det = dot3(e1.x, e1.y, e1.z, px, py, pz);
-        if (det == 0.0f) return;
-        float inv = __fdiv_rn(1.0f, det);
-        float sx = __fsub_rn(r.ox, v0.x), sy = __fsub_rn(r.oy, v0.y), sz = __fsub_rn(r.oz, v0.z);
-        float u = __fmul_rn(dot3(sx, sy, sz, px, py, pz), inv);
-        if (!(u >= 0.0f && u <= 1.0f)) return;
-        float qx, qy, qz;
-        cross3(sx, sy, sz, e1.x, e1.y, e1.z, qx, qy, qz);
-        float v = __fmul_rn(dot3(r.dx, r.dy, r.dz, qx, qy, qz), inv);
-        if (!(v >= 0.0f && __fadd_rn(u, v) <= 1.0f)) return;
-        float t = __fmul_rn(dot3(e2.x, e2.y, e2.z, qx, qy, qz), inv);
-        consider(h, t, __float_as_int(v0.w), slot);
+        float4 r0, r1, r2;
+        cam_tri_record(v0, e1, e2, r.ox, r.oy, r.oz, r0, r1, r2);
+        tri_finish(h, r.dx, r.dy, r.dz, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r0.w, __float_as_int(v0.w), slot);
     } else {
         // v1 Sphere::hit in double on the float32 ray / sphere, roots rounded to float32
         float4 s = __ldg(sc.prims + slot);
@@ -291,6 +325,78 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
             else if (hr) tv.cur = rc;
             else trav_pop(tv, stack_code, stack_tn);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------- packet traversal
+// One warp = one packet of 32 camera rays (an 8x4 pixel block, one shared origin).  The warp walks
+// the UNION of its lanes' traversals with a single stack: at an internal node every lane slab-tests
+// both children against its own closest hit, ballots decide which children are entered at all and
+// which first (each lane votes for its nearer hit child), the other child is pushed with the
+// smallest entry distance of any lane (REDUX.MIN on the float bits, distances are positive) and is
+// dropped on pop when that exceeds every lane's closest hit (REDUX.MAX).  Node and primitive
+// addresses are warp-uniform, so each fetch is one broadcast request, no lane ever idles in
+// another lane's phase, and no per-lane stack exists: the stack lives in two registers per lane
+// (entry k in lane k & 31), pushed by a predicated move and popped by a shuffle.
+// Results are the per-ray traversal's bit for bit: every lane tests a superset of the primitives its
+// own walk would test, and closest-hit selection is order independent (consider()).
+// cnt.nodes / cnt.prims count what the PACKET fetched (lane 0 only), not per-ray visits.
+// inactive lanes (pixels outside the frame) carry closest hit 0 and never enter a box.
+template <bool TRI, bool STATS>
+__device__ __forceinline__ void packet_intersect(const SceneView& sc, const float4* __restrict__ cam_prims, const Ray& r,
+                                                 bool active, int lane, Hit& h, Counters& cnt) {
+    h.t = active ? kTMax : 0.0f; h.prim = -1; h.slot = -1;
+    if (sc.n_nodes == 0) return;
+    float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
+    float tn;
+    if (STATS && lane == 0) cnt.nodes += 1;
+    bool hit = box_hit(lo, hi, r, kTMin, h.t, tn);
+    if (!__any_sync(0xffffffffu, hit)) return;
+    int cur = node_code(__float_as_int(lo.w), __float_as_int(hi.w));
+    int st0 = 0, st1 = 0;
+    unsigned stt0 = 0u, stt1 = 0u;
+    int sp = 0;
+    for (;;) {
+        if (cur >= 0) {
+            const float4* p = sc.nodes + 2 * (size_t)cur;
+            float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
+            if (STATS && lane == 0) cnt.nodes += 2;
+            float tl, tr;
+            bool hl = box_hit(l0, l1, r, kTMin, h.t, tl);
+            bool hr = box_hit(r0, r1, r, kTMin, h.t, tr);
+            const unsigned bl = __ballot_sync(0xffffffffu, hl), br = __ballot_sync(0xffffffffu, hr);
+            const int lc = node_code(__float_as_int(l0.w), __float_as_int(l1.w));
+            const int rc = node_code(__float_as_int(r0.w), __float_as_int(r1.w));
+            if (bl != 0u && br != 0u) {
+                const unsigned vr = __ballot_sync(0xffffffffu, hr && (!hl || tr < tl));
+                const bool right_first = 2 * __popc(vr) > __popc(bl | br);
+                const float tfar = right_first ? (hl ? tl : __int_as_float(0x7f800000)) : (hr ? tr : __int_as_float(0x7f800000));
+                const unsigned tf = __reduce_min_sync(0xffffffffu, __float_as_uint(tfar));
+                const int far = right_first ? lc : rc;
+                if (lane == (sp & 31)) { if (sp < 32) { st0 = far; stt0 = tf; } else { st1 = far; stt1 = tf; } }
+                ++sp;
+                cur = right_first ? rc : lc;
+                continue;
+            } else if (bl != 0u) { cur = lc; continue; }
+            else if (br != 0u) { cur = rc; continue; }
+        } else {
+            const int code = ~cur;
+            const int first = code >> 3, count = code & 7;
+            if (STATS && lane == 0) cnt.prims += count;
+            for (int k = 0; k < count; ++k) {
+                if (TRI) test_cam_tri(cam_prims, first + k, r, h);
+                else test_prim<false>(sc, first + k, r, h);
+            }
+        }
+        const unsigned max_t = __reduce_max_sync(0xffffffffu, __float_as_uint(h.t));
+        bool found = false;
+        while (sp > 0) {
+            --sp;
+            const int c = __shfl_sync(0xffffffffu, sp < 32 ? st0 : st1, sp & 31);
+            const unsigned t = __shfl_sync(0xffffffffu, sp < 32 ? stt0 : stt1, sp & 31);
+            if (t <= max_t) { cur = c; found = true; break; }
+        }
+        if (!found) break;
     }
 }
 

@@ -212,6 +212,72 @@ k_path(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
     if (STATS) flush_stats(d_stats, rays, cnt);
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_cam_tris: per-frame table of camera-relative triangle records (rt_device.cuh cam_tri_record) for
+// the shared origin of all camera rays: 48 B read + 48 B written per triangle, HBM-streaming.
+__global__ void __launch_bounds__(256)
+k_cam_tris(const float4* __restrict__ prims, float4* __restrict__ cam_prims, int n, float ox, float oy, float oz) {
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        const float4* p = prims + 3 * (size_t)slot;
+        float4 r0, r1, r2;
+        cam_tri_record(__ldg(p), __ldg(p + 1), __ldg(p + 2), ox, oy, oz, r0, r1, r2);
+        float4* o = cam_prims + 3 * (size_t)slot;
+        o[0] = r0; o[1] = r1; o[2] = r2;
+    }
+}
+
+// k_packet: camera rays only (max_depth 1 renders and the primary-hit AOV).  One warp = one 8x4
+// pixel block = one packet walking the BVH with packet_intersect(); persistent warps pull blocks
+// from the global counter.  Shading of a single-segment path is emission or background.
+template <bool TRI, bool STATS, bool AOV>
+__global__ void __launch_bounds__(kThreads)
+k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_prims, const __grid_constant__ CameraBlock cam,
+         const __grid_constant__ TileMap tm, int n_work, int spp, uint32_t k0, uint32_t k1, uint32_t sample_offset,
+         int resolve, float* __restrict__ d_out, int32_t* __restrict__ d_prim, float* __restrict__ d_t,
+         unsigned int* counter, unsigned long long* d_stats) {
+    const int lane = threadIdx.x & 31;
+    const double inv_w = __ddiv_rn(1.0, (double)tm.width), inv_h = __ddiv_rn(1.0, (double)tm.height);
+    const float inv_spp = __fdiv_rn(1.0f, (float)spp);
+    Counters cnt = {0, 0, 0};
+    unsigned long long rays = 0;
+    for (;;) {
+        int w = next_work(counter, lane);
+        if (w >= n_work) break;
+        PixelWork p = decode_work(tm, w, lane);
+        const uint32_t pixel = (uint32_t)(p.j * tm.width + p.i);
+        float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+        for (int s = 0; s < spp; ++s) {
+            float jx = 0.5f, jy = 0.5f;
+            if (!AOV) {
+                uint4 ctl = philox4x32_10(pixel, sample_offset + (uint32_t)s, 0u, 0u, k0, k1);
+                jx = u01(ctl.x); jy = u01(ctl.y);
+            }
+            Ray r = camera_ray(cam, p.i, p.j, jx, jy, inv_w, inv_h);
+            Hit h;
+            packet_intersect<TRI, STATS>(sc, cam_prims, r, p.active, lane, h, cnt);
+            if (STATS && p.active) { rays += 1; cnt.segments += 1; }
+            if (AOV) {
+                if (p.active) { d_prim[p.out_index] = h.prim; d_t[p.out_index] = h.prim >= 0 ? h.t : 0.0f; }
+            } else {
+                float cr = 0.0f, cg = 0.0f, cb = 0.0f;
+                if (h.prim < 0) {
+                    cr = __fmaf_rn(1.0f, sc.bg_r, cr); cg = __fmaf_rn(1.0f, sc.bg_g, cg); cb = __fmaf_rn(1.0f, sc.bg_b, cb);
+                } else {
+                    float4 m1 = __ldg(sc.mats + 2 * (size_t)material_row<TRI>(sc, h) + 1);
+                    cr = __fmaf_rn(1.0f, m1.y, cr); cg = __fmaf_rn(1.0f, m1.z, cg); cb = __fmaf_rn(1.0f, m1.w, cb);
+                }
+                sr = __fadd_rn(sr, cr); sg = __fadd_rn(sg, cg); sb = __fadd_rn(sb, cb);
+            }
+        }
+        if (!AOV && p.active) {
+            float* o = d_out + 3 * (size_t)p.out_index;
+            if (resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
+            else { o[0] = sr; o[1] = sg; o[2] = sb; }
+        }
+    }
+    if (STATS) flush_stats(d_stats, rays, cnt);
+}
+
 __global__ void k_untile(int width, int height, int tile_w, int tile_h, int tiles_x, int n_ranks, int tiles_per_rank,
                          const float* __restrict__ tiles, float* __restrict__ frame) {
     int64_t n = (int64_t)width * height;
@@ -267,6 +333,25 @@ cudaError_t launch_path(const SceneView& sc, const CameraBlock& cam, const TileM
     return cudaGetLastError();
 }
 
+template <bool TRI, bool STATS, bool AOV>
+cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const TileMap& tm, int spp, uint64_t seed,
+                          uint32_t sample_offset, int resolve, float* d_out, int32_t* d_prim, float* d_t,
+                          const LaunchCfg& cfg) {
+    int n_work = work_items(tm);
+    if (TRI && sc.n_prims > 0) {
+        int64_t g = ((int64_t)sc.n_prims + 255) / 256;
+        int cap = cfg.sm_count * 8;
+        k_cam_tris<<<(int)(g > cap ? cap : g), 256, 0, cfg.stream>>>(sc.prims, cfg.d_cam_prims, sc.n_prims, cam.px, cam.py, cam.pz);
+    }
+    int grid = resident_grid(k_packet<TRI, STATS, AOV>, cfg.sm_count);
+    int need = (n_work + (kThreads / 32) - 1) / (kThreads / 32);
+    if (grid > need) grid = need;
+    k_packet<TRI, STATS, AOV><<<grid, kThreads, 0, cfg.stream>>>(
+        sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
+        d_prim, d_t, cfg.d_work_counter, cfg.d_stats);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
@@ -276,6 +361,12 @@ cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraB
     cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
     if (e != cudaSuccess) return e;
     bool st = cfg.d_stats != nullptr;
+    if (cfg.variant == 3) {
+        if (is_tri) return st ? launch_packet<true, true, true>(sc, cam, tm, 1, 0, 0, 0, nullptr, d_prim, d_t, cfg)
+                              : launch_packet<true, false, true>(sc, cam, tm, 1, 0, 0, 0, nullptr, d_prim, d_t, cfg);
+        return st ? launch_packet<false, true, true>(sc, cam, tm, 1, 0, 0, 0, nullptr, d_prim, d_t, cfg)
+                  : launch_packet<false, false, true>(sc, cam, tm, 1, 0, 0, 0, nullptr, d_prim, d_t, cfg);
+    }
     if (cfg.variant == 0) {
         if (is_tri) return st ? launch_path<true, true, true>(sc, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t, cfg)
                               : launch_path<true, false, true>(sc, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t, cfg);
@@ -321,7 +412,13 @@ cudaError_t launch_render(const SceneView& sc, bool is_tri, const CameraBlock& c
     cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
     if (e != cudaSuccess) return e;
     bool st = cfg.d_stats != nullptr;
-    if (cfg.variant == 0) {
+    if (cfg.variant == 3 && max_depth == 1) {
+        if (is_tri) return st ? launch_packet<true, true, false>(sc, cam, tm, spp, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg)
+                              : launch_packet<true, false, false>(sc, cam, tm, spp, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg);
+        return st ? launch_packet<false, true, false>(sc, cam, tm, spp, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg)
+                  : launch_packet<false, false, false>(sc, cam, tm, spp, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg);
+    }
+    if (cfg.variant == 0 || cfg.variant == 3) {
         if (is_tri) return st ? launch_path<true, true, false>(sc, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg)
                               : launch_path<true, false, false>(sc, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg);
         return st ? launch_path<false, true, false>(sc, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg)

@@ -23,7 +23,9 @@ struct LaunchCfg {
     int sm_count;
     unsigned int* d_work_counter;            // zeroed by the launcher on `stream`
     unsigned long long* d_stats;             // [rays, segments, node_records, prim_tests] or nullptr
-    int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel, 2 = wavefront
+    int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel, 2 = wavefront,
+                                             // 3 = k_packet (camera rays: warp = packet with one shared stack)
+    float4* d_cam_prims;                     // per-frame camera-relative triangle records (3 x float4 per slot)
     int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes
     int leaf_vote;                           // phase voting: leaf step when >= this many lanes hold a leaf
 };
