@@ -178,8 +178,11 @@ int ensure_device(rt_ctx* ctx) {
         if (ctx->is_tri) CK(cudaMalloc(&ctx->d_cam_prims, prims.size() * sizeof(float4)));
         CK(cudaMalloc(&ctx->d_slot_prim, (size_t)n * sizeof(int)));
         CK(cudaMemcpy(ctx->d_slot_prim, ctx->prim_index.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        // device node = bmin | code, bmax | 0: code >= 0 child-pair index, code <= -2 leaf ~((first << 3) | count)
+        std::vector<rt_bvh_node> dn(ctx->nodes);
+        for (auto& nd : dn) { nd.a = nd.b == 0 ? nd.a : ~((nd.a << 3) | nd.b); nd.b = 0; }
         CK(cudaMalloc(&ctx->d_nodes, (size_t)n_nodes * sizeof(rt_bvh_node)));
-        CK(cudaMemcpy(ctx->d_nodes, ctx->nodes.data(), (size_t)n_nodes * sizeof(rt_bvh_node), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_nodes, dn.data(), (size_t)n_nodes * sizeof(rt_bvh_node), cudaMemcpyHostToDevice));
     }
     const int m = ctx->m;
     if (m > 0) {
@@ -205,6 +208,12 @@ SceneView scene_view(const rt_ctx* c) {
     SceneView v;
     v.nodes = c->d_nodes; v.prims = c->d_prims; v.slot_prim = c->d_slot_prim; v.mats = c->d_mats;
     v.n_prims = (int)c->n; v.n_nodes = (int)c->nodes.size();
+    v.sane_extent = 0;
+    if (!c->nodes.empty()) {
+        float mx = 0.0f;
+        for (int k = 0; k < 3; ++k) mx = std::fmax(mx, std::fmax(std::fabs(c->nodes[0].bmin[k]), std::fabs(c->nodes[0].bmax[k])));
+        v.sane_extent = mx < 0x1p40f ? 1 : 0;      // NaN compares false
+    }
     v.bg_r = c->bg[0]; v.bg_g = c->bg[1]; v.bg_b = c->bg[2];
     return v;
 }

@@ -33,12 +33,13 @@ struct CameraBlock {              // basis in double: primary directions are rou
 };
 
 struct SceneView {
-    const float4* __restrict__ nodes;      // 2 x float4 per 32-byte node (rt_bvh_node)
+    const float4* __restrict__ nodes;      // 2 x float4 per 32-byte node: bmin | code, bmax | 0 (see intersect())
     const float4* __restrict__ prims;      // leaf order; triangle: v0|prim, e1|material, e2|0 ; sphere: c|r
     const int* __restrict__ slot_prim;     // slot -> primitive number (upload order)
     const float4* __restrict__ mats;       // 2 x float4 per material: albedo|metallic, roughness|emission
     int n_prims;
     int n_nodes;
+    int sane_extent;                       // every |coordinate| of the root box < 2^40 (octant slab test usable)
     float bg_r, bg_g, bg_b;
 };
 
@@ -197,6 +198,11 @@ __device__ __forceinline__ void test_prim(const SceneView& sc, int slot, const R
     }
 }
 
+// Device node records (written by the upload in rt_api.cu from the host rt_bvh_node array):
+// float4 (bmin | code), float4 (bmax | 0) with code >= 0: internal, index of the child pair (children at
+// code, code + 1; a pair is 64-byte aligned); code <= -2: leaf, ~code = (first_slot << 3) | count.
+constexpr int kDone = -1;
+
 // Closest hit over the flattened BVH: sibling pairs fetched as 4 x LDG.128 (ld.global.nc.v4),
 // nearer child first, farther child pushed with its entry distance, dropped on pop when that
 // distance exceeds the closest hit.  (Same visiting order as oracle MODE_NEAR_FIRST, so the
@@ -209,44 +215,38 @@ __device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit
     float tn;
     if (STATS) cnt.nodes += 1;
     if (!box_hit(lo, hi, r, kTMin, h.t, tn)) return;
-    int ca = __float_as_int(lo.w), cb = __float_as_int(hi.w);
+    int cur = __float_as_int(lo.w);
     int stack_code[kStackDepth];
     float stack_tn[kStackDepth];
     int sp = 0;
     for (;;) {
-        if (cb == 0) {
-            const float4* p = sc.nodes + 2 * (size_t)ca;
+        if (cur >= 0) {
+            const float4* p = sc.nodes + 2 * (size_t)cur;
             float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
             if (STATS) cnt.nodes += 2;
             float tl, tr;
             bool hl = box_hit(l0, l1, r, kTMin, h.t, tl);
             bool hr = box_hit(r0, r1, r, kTMin, h.t, tr);
-            int la = __float_as_int(l0.w), lb = __float_as_int(l1.w);
-            int ra = __float_as_int(r0.w), rb = __float_as_int(r1.w);
+            int lc = __float_as_int(l0.w), rc = __float_as_int(r0.w);
             if (hl && hr) {
-                if (tr < tl) { int t0 = la; la = ra; ra = t0; t0 = lb; lb = rb; rb = t0; float tf = tl; tl = tr; tr = tf; }
-                stack_code[sp] = rb == 0 ? ra : ~((ra << 3) | rb);
-                stack_tn[sp] = tr;
-                ++sp;
-                ca = la; cb = lb;
+                if (tr < tl) { int c = lc; lc = rc; rc = c; float tf = tl; tl = tr; tr = tf; }
+                stack_code[sp] = rc; stack_tn[sp] = tr; ++sp;
+                cur = lc;
                 continue;
-            } else if (hl) { ca = la; cb = lb; continue; }
-            else if (hr) { ca = ra; cb = rb; continue; }
+            } else if (hl) { cur = lc; continue; }
+            else if (hr) { cur = rc; continue; }
         } else {
-            for (int k = 0; k < cb; ++k) {
+            const int code = ~cur;
+            const int first = code >> 3, count = code & 7;
+            for (int k = 0; k < count; ++k) {
                 if (STATS) cnt.prims += 1;
-                test_prim<TRI>(sc, ca + k, r, h);
+                test_prim<TRI>(sc, first + k, r, h);
             }
         }
         bool found = false;
         while (sp > 0) {
             --sp;
-            if (stack_tn[sp] <= h.t) {
-                int code = stack_code[sp];
-                if (code >= 0) { ca = code; cb = 0; } else { code = ~code; ca = code >> 3; cb = code & 7; }
-                found = true;
-                break;
-            }
+            if (stack_tn[sp] <= h.t) { cur = stack_code[sp]; found = true; break; }
         }
         if (!found) break;
     }
@@ -255,13 +255,10 @@ __device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit
 // ------------------------------------------------------------------------------- resumable traversal
 // The same walk as intersect(), cut into a per-lane state (Trav + a local-memory stack) so that a
 // warp can leave the traversal loop when too few of its lanes still have work, shade / refill the
-// finished lanes, and come back.  Node codes: >= 0 internal (index of the child pair), <= -2 leaf
-// (~((first_slot << 3) | count)), kDone = -1.  The per-ray visiting order is exactly intersect()'s.
-constexpr int kDone = -1;
+// finished lanes, and come back.  Node codes as above, kDone = -1 = no node.  The per-ray visiting
+// order is exactly intersect()'s.
 
 struct Trav { int cur; int sp; Hit h; };
-
-__device__ __forceinline__ int node_code(int a, int b) { return b == 0 ? a : ~((a << 3) | b); }
 
 __device__ __forceinline__ void trav_pop(Trav& tv, const int* stack_code, const float* stack_tn) {
     while (tv.sp > 0) {
@@ -279,7 +276,7 @@ __device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Tr
     float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
     float tn;
     if (STATS) cnt.nodes += 1;
-    if (box_hit(lo, hi, r, kTMin, tv.h.t, tn)) tv.cur = node_code(__float_as_int(lo.w), __float_as_int(hi.w));
+    if (box_hit(lo, hi, r, kTMin, tv.h.t, tn)) tv.cur = __float_as_int(lo.w);
 }
 
 // Runs the warp's traversals until fewer than `min_active` lanes still have work (warp-uniform call).
@@ -315,8 +312,8 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
             float tl, tr;
             bool hl = box_hit(l0, l1, r, kTMin, tv.h.t, tl);
             bool hr = box_hit(r0, r1, r, kTMin, tv.h.t, tr);
-            int lc = node_code(__float_as_int(l0.w), __float_as_int(l1.w));
-            int rc = node_code(__float_as_int(r0.w), __float_as_int(r1.w));
+            int lc = __float_as_int(l0.w);
+            int rc = __float_as_int(r0.w);
             if (hl && hr) {
                 if (tr < tl) { int c = lc; lc = rc; rc = c; float tf = tl; tl = tr; tr = tf; }
                 stack_code[tv.sp] = rc; stack_tn[tv.sp] = tr; ++tv.sp;
@@ -333,47 +330,70 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
 // the UNION of its lanes' traversals with a single stack: at an internal node every lane slab-tests
 // both children against its own closest hit, ballots decide which children are entered at all and
 // which first (each lane votes for its nearer hit child), the other child is pushed with the
-// smallest entry distance of any lane (REDUX.MIN on the float bits, distances are positive) and is
-// dropped on pop when that exceeds every lane's closest hit (REDUX.MAX).  Node and primitive
-// addresses are warp-uniform, so each fetch is one broadcast request, no lane ever idles in
-// another lane's phase, and no per-lane stack exists: the stack lives in two registers per lane
-// (entry k in lane k & 31), pushed by a predicated move and popped by a shuffle.
+// smallest entry distance of any lane (CREDUX.MIN on the float bits, distances are positive) and is
+// dropped on pop when that exceeds every lane's closest hit (CREDUX.MAX).  Node and primitive
+// addresses are warp-uniform, so each fetch is one broadcast request, no lane ever idles in another
+// lane's phase, and no per-lane stack exists: the warp's stack is 64 x 8 bytes of shared memory that
+// every lane writes / reads at the same address (no bank conflict, no synchronisation needed: a lane
+// reads back what it wrote itself).
 // Results are the per-ray traversal's bit for bit: every lane tests a superset of the primitives its
 // own walk would test, and closest-hit selection is order independent (consider()).
 // cnt.nodes / cnt.prims count what the PACKET fetched (lane 0 only), not per-ray visits.
 // inactive lanes (pixels outside the frame) carry closest hit 0 and never enter a box.
-template <bool TRI, bool STATS>
-__device__ __forceinline__ void packet_intersect(const SceneView& sc, const float4* __restrict__ cam_prims, const Ray& r,
-                                                 bool active, int lane, Hit& h, Counters& cnt) {
-    h.t = active ? kTMax : 0.0f; h.prim = -1; h.slot = -1;
-    if (sc.n_nodes == 0) return;
-    float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
-    float tn;
-    if (STATS && lane == 0) cnt.nodes += 1;
-    bool hit = box_hit(lo, hi, r, kTMin, h.t, tn);
-    if (!__any_sync(0xffffffffu, hit)) return;
-    int cur = node_code(__float_as_int(lo.w), __float_as_int(hi.w));
-    int st0 = 0, st1 = 0;
-    unsigned stt0 = 0u, stt1 = 0u;
+//
+// OCT in 0..7: every lane's direction has the sign pattern OCT (bit k set = component k negative) and
+// no component is tiny, so the near / far plane of each slab is known at compile time and the slab
+// test needs no per-axis min / max (4 instead of 10 FMNMX-pipe instructions per box; that pipe, not
+// FFMA, limits the traversal).  fmaf is monotonic, so picking the plane by sign gives exactly the
+// value fminf / fmaxf would pick: same bits as box_hit().  OCT = 8: generic test.
+template <int OCT>
+__device__ __forceinline__ bool box_hit_oct(const float4& lo, const float4& hi, const Ray& r, float tlo, float thi, float& tn) {
+    if (OCT == 8) return box_hit(lo, hi, r, tlo, thi, tn);
+    const float nx = (OCT & 1) ? hi.x : lo.x, fx = (OCT & 1) ? lo.x : hi.x;
+    const float ny = (OCT & 2) ? hi.y : lo.y, fy = (OCT & 2) ? lo.y : hi.y;
+    const float nz = (OCT & 4) ? hi.z : lo.z, fz = (OCT & 4) ? lo.z : hi.z;
+    float n = fmaxf(fmaxf(__fmaf_rn(nx, r.ix, -r.ax), __fmaf_rn(ny, r.iy, -r.ay)), fmaxf(__fmaf_rn(nz, r.iz, -r.az), tlo));
+    float f = fminf(fminf(__fmaf_rn(fx, r.ix, -r.ax), __fmaf_rn(fy, r.iy, -r.ay)), fminf(__fmaf_rn(fz, r.iz, -r.az), thi));
+    tn = n;
+    return n <= f;
+}
+
+// camera route of the triangle test for a packet: all three record loads issued up front, one
+// combined predicate (det == 0 fails `det > 0` after the sign flip), sign flip as a multiplication
+// by +-1 (exact) so that it runs on the FFMA pipe.  Same bits as test_cam_tri().
+__device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ cam_prims, int slot, const Ray& r, Hit& h) {
+    const float4* p = cam_prims + 3 * (size_t)slot;
+    const float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
+    float det = dot3(r.dx, r.dy, r.dz, r0.x, r0.y, r0.z);
+    float un = dot3(r.dx, r.dy, r.dz, r1.x, r1.y, r1.z);
+    float vn = dot3(r.dx, r.dy, r.dz, r2.x, r2.y, r2.z);
+    const float sg = det < 0.0f ? -1.0f : 1.0f;
+    det = __fmul_rn(det, sg); un = __fmul_rn(un, sg); vn = __fmul_rn(vn, sg);
+    if (det > 0.0f && un >= 0.0f && vn >= 0.0f && __fadd_rn(un, vn) <= det)
+        consider(h, __fdiv_rn(__fmul_rn(r0.w, sg), det), __float_as_int(r1.w), slot);
+}
+
+template <bool TRI, bool STATS, int OCT>
+__device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* __restrict__ cam_prims, const Ray& r, int lane,
+                                            uint2* __restrict__ stack, int cur, Hit& h, Counters& cnt) {
     int sp = 0;
     for (;;) {
         if (cur >= 0) {
             const float4* p = sc.nodes + 2 * (size_t)cur;
-            float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
+            const float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
             if (STATS && lane == 0) cnt.nodes += 2;
             float tl, tr;
-            bool hl = box_hit(l0, l1, r, kTMin, h.t, tl);
-            bool hr = box_hit(r0, r1, r, kTMin, h.t, tr);
+            const bool hl = box_hit_oct<OCT>(l0, l1, r, kTMin, h.t, tl);
+            const bool hr = box_hit_oct<OCT>(r0, r1, r, kTMin, h.t, tr);
             const unsigned bl = __ballot_sync(0xffffffffu, hl), br = __ballot_sync(0xffffffffu, hr);
-            const int lc = node_code(__float_as_int(l0.w), __float_as_int(l1.w));
-            const int rc = node_code(__float_as_int(r0.w), __float_as_int(r1.w));
+            const int lc = __float_as_int(l0.w), rc = __float_as_int(r0.w);
             if (bl != 0u && br != 0u) {
-                const unsigned vr = __ballot_sync(0xffffffffu, hr && (!hl || tr < tl));
+                // entry distances with +inf for a missed child: a lane votes "right first" iff tr' < tl'
+                const float tl2 = hl ? tl : __int_as_float(0x7f800000), tr2 = hr ? tr : __int_as_float(0x7f800000);
+                const unsigned vr = __ballot_sync(0xffffffffu, tr2 < tl2);
                 const bool right_first = 2 * __popc(vr) > __popc(bl | br);
-                const float tfar = right_first ? (hl ? tl : __int_as_float(0x7f800000)) : (hr ? tr : __int_as_float(0x7f800000));
-                const unsigned tf = __reduce_min_sync(0xffffffffu, __float_as_uint(tfar));
-                const int far = right_first ? lc : rc;
-                if (lane == (sp & 31)) { if (sp < 32) { st0 = far; stt0 = tf; } else { st1 = far; stt1 = tf; } }
+                const unsigned tf = __reduce_min_sync(0xffffffffu, __float_as_uint(right_first ? tl2 : tr2));
+                stack[sp] = make_uint2((unsigned)(right_first ? lc : rc), tf);
                 ++sp;
                 cur = right_first ? rc : lc;
                 continue;
@@ -384,7 +404,7 @@ __device__ __forceinline__ void packet_intersect(const SceneView& sc, const floa
             const int first = code >> 3, count = code & 7;
             if (STATS && lane == 0) cnt.prims += count;
             for (int k = 0; k < count; ++k) {
-                if (TRI) test_cam_tri(cam_prims, first + k, r, h);
+                if (TRI) test_cam_tri_packet(cam_prims, first + k, r, h);
                 else test_prim<false>(sc, first + k, r, h);
             }
         }
@@ -392,11 +412,40 @@ __device__ __forceinline__ void packet_intersect(const SceneView& sc, const floa
         bool found = false;
         while (sp > 0) {
             --sp;
-            const int c = __shfl_sync(0xffffffffu, sp < 32 ? st0 : st1, sp & 31);
-            const unsigned t = __shfl_sync(0xffffffffu, sp < 32 ? stt0 : stt1, sp & 31);
-            if (t <= max_t) { cur = c; found = true; break; }
+            const uint2 e = stack[sp];
+            if (e.y <= max_t) { cur = (int)e.x; found = true; break; }
         }
         if (!found) break;
+    }
+}
+
+template <bool TRI, bool STATS>
+__device__ __forceinline__ void packet_intersect(const SceneView& sc, const float4* __restrict__ cam_prims, const Ray& r,
+                                                 bool active, int lane, uint2* __restrict__ stack, Hit& h, Counters& cnt) {
+    h.t = active ? kTMax : 0.0f; h.prim = -1; h.slot = -1;
+    if (sc.n_nodes == 0) return;
+    const float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
+    float tn;
+    if (STATS && lane == 0) cnt.nodes += 1;
+    const bool hit = box_hit(lo, hi, r, kTMin, h.t, tn);
+    if (!__any_sync(0xffffffffu, hit)) return;
+    const int root = __float_as_int(lo.w);
+    // octant of the packet: sign bits of the direction; usable when all lanes agree, no component is
+    // tiny (so 1/d, o/d and every slab product stay finite) and the scene is of sane extent
+    const int oct = (r.dx < 0.0f ? 1 : 0) | (r.dy < 0.0f ? 2 : 0) | (r.dz < 0.0f ? 4 : 0);
+    const bool tiny = !(fabsf(r.dx) >= 0x1p-60f && fabsf(r.dy) >= 0x1p-60f && fabsf(r.dz) >= 0x1p-60f);
+    const int oct0 = __shfl_sync(0xffffffffu, oct, 0);
+    const bool uniform = sc.sane_extent && __all_sync(0xffffffffu, oct == oct0 && !tiny);
+    if (!uniform) { packet_walk<TRI, STATS, 8>(sc, cam_prims, r, lane, stack, root, h, cnt); return; }
+    switch (oct0) {
+        case 0: packet_walk<TRI, STATS, 0>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
+        case 1: packet_walk<TRI, STATS, 1>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
+        case 2: packet_walk<TRI, STATS, 2>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
+        case 3: packet_walk<TRI, STATS, 3>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
+        case 4: packet_walk<TRI, STATS, 4>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
+        case 5: packet_walk<TRI, STATS, 5>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
+        case 6: packet_walk<TRI, STATS, 6>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
+        default: packet_walk<TRI, STATS, 7>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
     }
 }
 

@@ -227,22 +227,61 @@ k_cam_tris(const float4* __restrict__ prims, float4* __restrict__ cam_prims, int
 }
 
 // k_packet: camera rays only (max_depth 1 renders and the primary-hit AOV).  One warp = one 8x4
-// pixel block = one packet walking the BVH with packet_intersect(); persistent warps pull blocks
-// from the global counter.  Shading of a single-segment path is emission or background.
+// pixel block = one packet walking the BVH with packet_intersect().  Work distribution keeps the
+// packets that are in flight on one SM next to each other in the image, so that they share the node
+// and triangle lines they pull into that SM's L1: a CTA (8 warps) owns one CHUNK of kChunk
+// consecutive blocks at a time (a 32x8-pixel strip); its warps take blocks from the chunk through a
+// shared-memory word (chunk << 8 | next offset, one ATOMS per block), and the warp that takes the
+// last offset + 1 fetches the CTA's next chunk from the global counter (one ATOMG per chunk) while
+// the others that run out wait for the word to change.  No CTA barrier, no fixed assignment: load
+// stays balanced to within one block per warp.
+constexpr int kPacketThreads = 256;
+constexpr int kChunk = 8;
+constexpr unsigned kNoChunk = 0xFFFFFFu;
+
+__device__ __forceinline__ int chunk_next_block(unsigned* word, unsigned int* global_counter, int n_chunks, int lane) {
+    unsigned v = 0xFFFFFFFFu;
+    if (lane == 0) {
+        for (;;) {
+            const unsigned old = atomicAdd(word, 1u);
+            const unsigned chunk = old >> 8, off = old & 0xFFu;
+            if (chunk == kNoChunk) break;
+            if (off < (unsigned)kChunk) { v = chunk * kChunk + off; break; }
+            if (off == (unsigned)kChunk) {                       // this warp installs the next chunk
+                const unsigned c = atomicAdd(global_counter, 1u);
+                atomicExch(word, (c < (unsigned)n_chunks ? c : kNoChunk) << 8);
+                continue;
+            }
+            while ((*(volatile unsigned*)word >> 8) == chunk) __nanosleep(32);
+        }
+    }
+    return (int)__shfl_sync(0xffffffffu, v, 0);
+}
+
 template <bool TRI, bool STATS, bool AOV>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kPacketThreads)
 k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_prims, const __grid_constant__ CameraBlock cam,
          const __grid_constant__ TileMap tm, int n_work, int spp, uint32_t k0, uint32_t k1, uint32_t sample_offset,
          int resolve, float* __restrict__ d_out, int32_t* __restrict__ d_prim, float* __restrict__ d_t,
          unsigned int* counter, unsigned long long* d_stats) {
+    __shared__ uint2 s_stack[kPacketThreads / 32][kStackDepth];
+    __shared__ unsigned s_word;
     const int lane = threadIdx.x & 31;
+    uint2* stack = s_stack[threadIdx.x >> 5];
+    const int n_chunks = (n_work + kChunk - 1) / kChunk;
+    if (threadIdx.x == 0) {
+        const unsigned c = atomicAdd(counter, 1u);
+        s_word = (c < (unsigned)n_chunks ? c : kNoChunk) << 8;
+    }
+    __syncthreads();
     const double inv_w = __ddiv_rn(1.0, (double)tm.width), inv_h = __ddiv_rn(1.0, (double)tm.height);
     const float inv_spp = __fdiv_rn(1.0f, (float)spp);
     Counters cnt = {0, 0, 0};
     unsigned long long rays = 0;
     for (;;) {
-        int w = next_work(counter, lane);
-        if (w >= n_work) break;
+        const int w = chunk_next_block(&s_word, counter, n_chunks, lane);
+        if (w < 0) break;
+        if (w >= n_work) continue;
         PixelWork p = decode_work(tm, w, lane);
         const uint32_t pixel = (uint32_t)(p.j * tm.width + p.i);
         float sr = 0.0f, sg = 0.0f, sb = 0.0f;
@@ -254,7 +293,7 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
             }
             Ray r = camera_ray(cam, p.i, p.j, jx, jy, inv_w, inv_h);
             Hit h;
-            packet_intersect<TRI, STATS>(sc, cam_prims, r, p.active, lane, h, cnt);
+            packet_intersect<TRI, STATS>(sc, cam_prims, r, p.active, lane, stack, h, cnt);
             if (STATS && p.active) { rays += 1; cnt.segments += 1; }
             if (AOV) {
                 if (p.active) { d_prim[p.out_index] = h.prim; d_t[p.out_index] = h.prim >= 0 ? h.t : 0.0f; }
@@ -343,10 +382,12 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
         int cap = cfg.sm_count * 8;
         k_cam_tris<<<(int)(g > cap ? cap : g), 256, 0, cfg.stream>>>(sc.prims, cfg.d_cam_prims, sc.n_prims, cam.px, cam.py, cam.pz);
     }
-    int grid = resident_grid(k_packet<TRI, STATS, AOV>, cfg.sm_count);
-    int need = (n_work + (kThreads / 32) - 1) / (kThreads / 32);
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_packet<TRI, STATS, AOV>, kPacketThreads, 0);
+    int grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);
+    int need = (n_work + kChunk - 1) / kChunk;
     if (grid > need) grid = need;
-    k_packet<TRI, STATS, AOV><<<grid, kThreads, 0, cfg.stream>>>(
+    k_packet<TRI, STATS, AOV><<<grid, kPacketThreads, 0, cfg.stream>>>(
         sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
         d_prim, d_t, cfg.d_work_counter, cfg.d_stats);
     return cudaGetLastError();
