@@ -3,7 +3,11 @@
 // fallback: every tracing entry point runs the sm_100a kernels of rt_kernels.cu.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -62,6 +66,19 @@ struct rt_ctx {
 
     float* d_fb = nullptr;                   // rt_render_host framebuffer
     size_t fb_floats = 0;
+    // rt_render_host copy/compute overlap (BandSignal): streams, per-band counters and host-mapped flags
+    cudaStream_t render_stream = nullptr, copy_stream = nullptr;
+    unsigned int* d_band_cnt = nullptr;
+    unsigned int* h_band_flags = nullptr;    // cudaHostAlloc mapped
+    unsigned int* d_band_flags = nullptr;    // device alias of h_band_flags
+    int overlap = 1;                         // option "overlap"
+    // cost-aware chunk order of the packet kernel (ChunkSchedule): history of the last frame of this tile map
+    int* d_chunk_order = nullptr;
+    unsigned int* d_chunk_cost = nullptr;
+    int chunk_cap = 0;
+    long long chunk_key = -1;
+    int schedule = 1;                        // option "schedule"
+    unsigned long long* d_block_times = nullptr;   // debug option "block_times" (device pointer supplied by the caller)
     int32_t* d_pick = nullptr;               // rt_select_object scratch: org3 dir3 | prim | t
 };
 
@@ -236,10 +253,42 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1) {
     cfg.variant = pick_kernel(c, max_depth);
     c->kernel_used = cfg.variant;
     cfg.d_cam_prims = c->d_cam_prims;
+    cfg.band = BandSignal{nullptr, nullptr, 0, 0, 1, 1, 1};
+    cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr};
+    cfg.d_block_times = c->stats ? c->d_block_times : nullptr;
     cfg.refill_below = c->refill;
     cfg.leaf_vote = c->leaf_vote;
     return cfg;
 }
+
+// Attach the chunk-cost history to a packet launch over tile map `tm` (ChunkSchedule).  The history is
+// only meaningful for the tile map it was recorded on; any other map starts from raster order.
+int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm) {
+    cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr};
+    if (!ctx->schedule || cfg.variant != 3) return 0;
+    const int n_chunks = packet_chunks(tm);
+    if (n_chunks <= 0) return 0;
+    if (n_chunks > ctx->chunk_cap) {
+        cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
+        ctx->d_chunk_order = nullptr; ctx->d_chunk_cost = nullptr; ctx->chunk_cap = 0; ctx->chunk_key = -1;
+        CK(cudaMalloc(&ctx->d_chunk_order, (size_t)n_chunks * sizeof(int)));
+        CK(cudaMalloc(&ctx->d_chunk_cost, (size_t)n_chunks * 2 * sizeof(unsigned int)));
+        ctx->chunk_cap = n_chunks;
+    }
+    long long key = ((((long long)tm.width * 65537 + tm.height) * 257 + tm.tile_w) * 257 + tm.tile_h) * 1031 + tm.first_tile;
+    key = key * 1031 + tm.tile_stride + 7919LL * tm.compact + 104729LL * tm.n_local_tiles;
+    if (key != ctx->chunk_key) {
+        CK(cudaMemsetAsync(ctx->d_chunk_cost, 0, (size_t)ctx->chunk_cap * 2 * sizeof(unsigned int), cfg.stream));
+        ctx->chunk_key = key;
+    }
+    cfg.sched.order = ctx->d_chunk_order;
+    cfg.sched.cost_sum = ctx->d_chunk_cost;
+    cfg.sched.cost_max = ctx->d_chunk_cost + ctx->chunk_cap;
+    return 0;
+}
+
+// launches of one packet-kernel call: k_chunk_order (if scheduled) + k_cam_tris (triangles) + k_packet
+int packet_launches(const rt_ctx* ctx, const LaunchCfg& cfg) { return 1 + (ctx->is_tri ? 1 : 0) + (cfg.sched.order ? 1 : 0); }
 
 TileMap full_frame_map(int width, int height) {
     TileMap tm;
@@ -300,6 +349,10 @@ void rt_destroy(rt_ctx* ctx) {
         free_device_scene(ctx);
         free_wave(ctx);
         cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick);
+        cudaFree(ctx->d_band_cnt); cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
+        if (ctx->h_band_flags) cudaFreeHost(ctx->h_band_flags);
+        if (ctx->render_stream) cudaStreamDestroy(ctx->render_stream);
+        if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     }
     delete ctx;
 }
@@ -448,8 +501,10 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
         ctx->launches += nl;
         return 0;
     }
-    CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, tm, d_prim, d_t, launch_cfg(ctx, stream)));
-    ctx->launches += (ctx->kernel_used == 3 && ctx->is_tri) ? 2 : 1;      // k_cam_tris + k_packet
+    LaunchCfg cfg = launch_cfg(ctx, stream);
+    if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, tm, d_prim, d_t, cfg));
+    ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
     return 0;
 }
 
@@ -519,9 +574,11 @@ int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, 
         ctx->launches += nl;
         return 0;
     }
+    LaunchCfg cfg = launch_cfg(ctx, stream, max_depth);
+    if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
-                     d_out, launch_cfg(ctx, stream, max_depth)));
-    if (tm.n_local_tiles) ctx->launches += (ctx->kernel_used == 3 && ctx->is_tri) ? 2 : 1;
+                     d_out, cfg));
+    if (tm.n_local_tiles) ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
     return 0;
 }
 
@@ -543,9 +600,11 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
         ctx->launches += nl;
         return 0;
     }
+    LaunchCfg cfg = launch_cfg(ctx, stream, max_depth);
+    if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
-                     d_out, launch_cfg(ctx, stream, max_depth)));
-    ctx->launches += (ctx->kernel_used == 3 && ctx->is_tri) ? 2 : 1;
+                     d_out, cfg));
+    ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
     return 0;
 }
 
@@ -583,18 +642,94 @@ int rt_untile(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int n_
     return 0;
 }
 
+constexpr int kMaxBands = 64;
+
+// Single-launch render with the device->host copy of finished regions overlapped (camera-ray packet
+// kernel only): see BandSignal in rt_kernels.h.  A region is a rectangle of 32x32 tiles, copied with one
+// cudaMemcpy2DAsync on a second stream as soon as the kernel raises the region's flag.
+static int render_host_overlapped(rt_ctx* ctx, int width, int height, int spp, uint64_t seed, uint32_t sample_offset,
+                                  float* h_out) {
+    if (!ctx->render_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->render_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaMalloc(&ctx->d_band_cnt, kMaxBands * sizeof(unsigned int)));
+        CK(cudaHostAlloc(&ctx->h_band_flags, kMaxBands * sizeof(unsigned int), cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer(&ctx->d_band_flags, ctx->h_band_flags, 0));
+    }
+    ctx->aspect = (double)width / height;
+    CameraBlock cam = camera_block(ctx, ctx->aspect);
+    TileMap tm = full_frame_map(width, height);
+    LaunchCfg cfg = launch_cfg(ctx, ctx->render_stream, 1);
+    BandSignal& bs = cfg.band;
+    bs.cnt = ctx->d_band_cnt;
+    bs.flags = ctx->d_band_flags;
+    bs.tiles_x = tm.tiles_x; bs.tiles_y = tm.n_tiles / tm.tiles_x;
+    int want_rows = 4, want_cols = 3;                              // 4 x 3 regions (each copy costs ~3.5 us of DMA idle; measured best on C3)
+    if (const char* e = std::getenv("B200RT_REGIONS")) std::sscanf(e, "%d,%d", &want_rows, &want_cols);
+    want_rows = std::max(1, std::min(want_rows, 16)); want_cols = std::max(1, std::min(want_cols, 4));
+    bs.band_rows = (bs.tiles_y + want_rows - 1) / want_rows;
+    bs.group_cols = (bs.tiles_x + want_cols - 1) / want_cols;
+    bs.n_groups = (bs.tiles_x + bs.group_cols - 1) / bs.group_cols;
+    const int n_regions = ((bs.tiles_y + bs.band_rows - 1) / bs.band_rows) * bs.n_groups;   // <= 48
+    if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    volatile unsigned int* flags = ctx->h_band_flags;
+    for (int b = 0; b < n_regions; ++b) flags[b] = 0u;
+    CK(cudaMemsetAsync(ctx->d_band_cnt, 0, kMaxBands * sizeof(unsigned int), ctx->render_stream));
+    CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, 1, ctx->integrator, seed, sample_offset, 1, ctx->d_fb, cfg));
+    ctx->launches += packet_launches(ctx, cfg);
+    static const bool trace = std::getenv("B200RT_TRACE") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
+    const size_t pitch = (size_t)width * 3 * sizeof(float);
+    bool copied[kMaxBands] = {false};
+    int n_copied = 0;
+    bool kernel_over = false;
+    while (n_copied < n_regions) {
+        bool any = false;
+        for (int b = 0; b < n_regions; ++b) {
+            if (copied[b] || (!kernel_over && flags[b] == 0u)) continue;
+            const int by = b / bs.n_groups, gx = b - by * bs.n_groups;
+            const int y0 = by * bs.band_rows * 32, y1 = std::min(height, (by + 1) * bs.band_rows * 32);
+            const int x0 = gx * bs.group_cols * 32, x1 = std::min(width, (gx + 1) * bs.group_cols * 32);
+            const size_t off = ((size_t)y0 * width + x0) * 3;
+            CK(cudaMemcpy2DAsync(h_out + off, pitch, ctx->d_fb + off, pitch, (size_t)(x1 - x0) * 3 * sizeof(float), (size_t)(y1 - y0),
+                                 cudaMemcpyDeviceToHost, ctx->copy_stream));
+            copied[b] = true; ++n_copied; any = true;
+            if (trace) std::fprintf(stderr, "region %d copy issued at %.0f us\n", b, us());
+        }
+        if (!any && !kernel_over) {
+            cudaError_t q = cudaStreamQuery(ctx->render_stream);    // kernel over (or failed): stop polling flags
+            if (q != cudaErrorNotReady) {
+                if (q != cudaSuccess) return cuda_fail(ctx, "rt_render_host: render", q);
+                kernel_over = true;
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(ctx->render_stream));
+    if (trace) std::fprintf(stderr, "render stream done at %.0f us\n", us());
+    CK(cudaStreamSynchronize(ctx->copy_stream));
+    if (trace) std::fprintf(stderr, "copy stream done at %.0f us\n", us());
+    return 0;
+}
+
 int rt_render_host(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
                    float* h_out) {
     if (!ctx) return 1;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (int rc = check_frame(ctx, width, height)) return rc;
     if (!h_out) return fail(ctx, "rt_render_host: NULL output");
+    if (spp <= 0 || max_depth < 0) return fail(ctx, "rt_render_host: bad arguments");
     DeviceGuard g(ctx->device);
     size_t need = (size_t)width * height * 3;
     if (need > ctx->fb_floats) {
         cudaFree(ctx->d_fb); ctx->d_fb = nullptr; ctx->fb_floats = 0;
         CK(cudaMalloc(&ctx->d_fb, need * sizeof(float)));
         ctx->fb_floats = need;
+    }
+    if (int rc = ensure_device(ctx)) return rc;
+    if (ctx->overlap && pick_kernel(ctx, max_depth) == 3 && max_depth == 1 && ctx->n > 0 && need >= ((size_t)1 << 18)) {
+        CK(cudaStreamSynchronize(nullptr));               // order after earlier work of the legacy stream
+        return render_host_overlapped(ctx, width, height, spp, seed, sample_offset, h_out);
     }
     if (int rc = rt_render(ctx, width, height, spp, max_depth, seed, sample_offset, ctx->d_fb, nullptr)) return rc;
     CK(cudaMemcpy(h_out, ctx->d_fb, need * sizeof(float), cudaMemcpyDeviceToHost));
@@ -629,6 +764,9 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "stats") ctx->stats = value != 0;
     else if (k == "kernel") { if (value < -1 || value > 3) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront) or 3 (camera-ray packets)"); ctx->kernel = (int)value; }
     else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
+    else if (k == "overlap") ctx->overlap = value != 0;
+    else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
+    else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);
     else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
     else return fail(ctx, "rt_set_option: unknown option '" + k + "'");
     return 0;
@@ -643,6 +781,8 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "kernel") *value = ctx->kernel;
     else if (k == "kernel_used") *value = ctx->kernel_used;
     else if (k == "refill") *value = ctx->refill;
+    else if (k == "overlap") *value = ctx->overlap;
+    else if (k == "schedule") *value = ctx->schedule;
     else if (k == "leaf_vote") *value = ctx->leaf_vote;
     else if (k == "sm_count") *value = ctx->sm_count;
     else if (k == "bvh_depth") *value = ctx->bvh_depth;

@@ -338,7 +338,8 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
 // reads back what it wrote itself).
 // Results are the per-ray traversal's bit for bit: every lane tests a superset of the primitives its
 // own walk would test, and closest-hit selection is order independent (consider()).
-// cnt.nodes / cnt.prims count what the PACKET fetched (lane 0 only), not per-ray visits.
+// cnt.nodes / cnt.prims count what the PACKET fetched (lane 0 only), not per-ray visits; `work` is the
+// packet's step count (internal steps + primitives tested), the scheduler's cost measure.
 // inactive lanes (pixels outside the frame) carry closest hit 0 and never enter a box.
 //
 // OCT in 0..7: every lane's direction has the sign pattern OCT (bit k set = component k negative) and
@@ -375,13 +376,14 @@ __device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ c
 
 template <bool TRI, bool STATS, int OCT>
 __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* __restrict__ cam_prims, const Ray& r, int lane,
-                                            uint2* __restrict__ stack, int cur, Hit& h, Counters& cnt) {
+                                            uint2* __restrict__ stack, int cur, Hit& h, Counters& cnt, int& work) {
     int sp = 0;
     for (;;) {
         if (cur >= 0) {
             const float4* p = sc.nodes + 2 * (size_t)cur;
             const float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
             if (STATS && lane == 0) cnt.nodes += 2;
+            work += 1;
             float tl, tr;
             const bool hl = box_hit_oct<OCT>(l0, l1, r, kTMin, h.t, tl);
             const bool hr = box_hit_oct<OCT>(r0, r1, r, kTMin, h.t, tr);
@@ -403,6 +405,7 @@ __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* _
             const int code = ~cur;
             const int first = code >> 3, count = code & 7;
             if (STATS && lane == 0) cnt.prims += count;
+            work += count;
             for (int k = 0; k < count; ++k) {
                 if (TRI) test_cam_tri_packet(cam_prims, first + k, r, h);
                 else test_prim<false>(sc, first + k, r, h);
@@ -421,7 +424,8 @@ __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* _
 
 template <bool TRI, bool STATS>
 __device__ __forceinline__ void packet_intersect(const SceneView& sc, const float4* __restrict__ cam_prims, const Ray& r,
-                                                 bool active, int lane, uint2* __restrict__ stack, Hit& h, Counters& cnt) {
+                                                 bool active, int lane, uint2* __restrict__ stack, Hit& h, Counters& cnt,
+                                                 int& work) {
     h.t = active ? kTMax : 0.0f; h.prim = -1; h.slot = -1;
     if (sc.n_nodes == 0) return;
     const float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
@@ -436,16 +440,16 @@ __device__ __forceinline__ void packet_intersect(const SceneView& sc, const floa
     const bool tiny = !(fabsf(r.dx) >= 0x1p-60f && fabsf(r.dy) >= 0x1p-60f && fabsf(r.dz) >= 0x1p-60f);
     const int oct0 = __shfl_sync(0xffffffffu, oct, 0);
     const bool uniform = sc.sane_extent && __all_sync(0xffffffffu, oct == oct0 && !tiny);
-    if (!uniform) { packet_walk<TRI, STATS, 8>(sc, cam_prims, r, lane, stack, root, h, cnt); return; }
+    if (!uniform) { packet_walk<TRI, STATS, 8>(sc, cam_prims, r, lane, stack, root, h, cnt, work); return; }
     switch (oct0) {
-        case 0: packet_walk<TRI, STATS, 0>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
-        case 1: packet_walk<TRI, STATS, 1>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
-        case 2: packet_walk<TRI, STATS, 2>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
-        case 3: packet_walk<TRI, STATS, 3>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
-        case 4: packet_walk<TRI, STATS, 4>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
-        case 5: packet_walk<TRI, STATS, 5>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
-        case 6: packet_walk<TRI, STATS, 6>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
-        default: packet_walk<TRI, STATS, 7>(sc, cam_prims, r, lane, stack, root, h, cnt); break;
+        case 0: packet_walk<TRI, STATS, 0>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
+        case 1: packet_walk<TRI, STATS, 1>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
+        case 2: packet_walk<TRI, STATS, 2>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
+        case 3: packet_walk<TRI, STATS, 3>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
+        case 4: packet_walk<TRI, STATS, 4>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
+        case 5: packet_walk<TRI, STATS, 5>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
+        case 6: packet_walk<TRI, STATS, 6>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
+        default: packet_walk<TRI, STATS, 7>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
     }
 }
 

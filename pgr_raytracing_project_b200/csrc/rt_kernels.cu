@@ -239,7 +239,14 @@ constexpr int kPacketThreads = 256;
 constexpr int kChunk = 8;
 constexpr unsigned kNoChunk = 0xFFFFFFu;
 
-__device__ __forceinline__ int chunk_next_block(unsigned* word, unsigned int* global_counter, int n_chunks, int lane) {
+__device__ __forceinline__ unsigned take_chunk(unsigned int* global_counter, int n_chunks, const int* __restrict__ order) {
+    const unsigned c = atomicAdd(global_counter, 1u);
+    if (c >= (unsigned)n_chunks) return kNoChunk << 8;
+    return (unsigned)(order ? order[c] : (int)c) << 8;
+}
+
+__device__ __forceinline__ int chunk_next_block(unsigned* word, unsigned int* global_counter, int n_chunks,
+                                                const int* __restrict__ order, int lane) {
     unsigned v = 0xFFFFFFFFu;
     if (lane == 0) {
         for (;;) {
@@ -248,8 +255,7 @@ __device__ __forceinline__ int chunk_next_block(unsigned* word, unsigned int* gl
             if (chunk == kNoChunk) break;
             if (off < (unsigned)kChunk) { v = chunk * kChunk + off; break; }
             if (off == (unsigned)kChunk) {                       // this warp installs the next chunk
-                const unsigned c = atomicAdd(global_counter, 1u);
-                atomicExch(word, (c < (unsigned)n_chunks ? c : kNoChunk) << 8);
+                atomicExch(word, take_chunk(global_counter, n_chunks, order));
                 continue;
             }
             while ((*(volatile unsigned*)word >> 8) == chunk) __nanosleep(32);
@@ -258,33 +264,89 @@ __device__ __forceinline__ int chunk_next_block(unsigned* word, unsigned int* gl
     return (int)__shfl_sync(0xffffffffu, v, 0);
 }
 
+// One CTA builds this frame's chunk order from last frame's costs (ChunkSchedule): latest-start-time
+// first.  A chunk's 8 blocks run side by side on the CTA's 8 warps, so its duration is its largest block
+// cost; the frame's length is T = (sum of all block costs) / resident warps; a chunk is due at T, or --
+// when finished regions are being copied out while the kernel runs (BandSignal) -- at the share of T at
+// which its region should be complete (regions in raster order).  key = due - duration, counting-sorted into 256 classes (order
+// inside a class is whatever the atomics give: pure scheduling, pixels do not depend on it).  With one
+// common due date this is longest-processing-time-first.  No history (all zero): raster order.
+__global__ void __launch_bounds__(1024)
+k_chunk_order(unsigned int* __restrict__ cost_sum, unsigned int* __restrict__ cost_max, int* __restrict__ order, int n,
+              int n_warps, const __grid_constant__ BandSignal band) {
+    __shared__ unsigned long long s_sum;
+    __shared__ unsigned int s_max;
+    __shared__ int s_hist[256];
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) { s_sum = 0ull; s_max = 0u; }
+    if (tid < 256) s_hist[tid] = 0;
+    __syncthreads();
+    unsigned long long part = 0;
+    unsigned int pm = 0;
+    for (int k = tid; k < n; k += 1024) { part += cost_sum[k]; pm = max(pm, cost_max[k]); }
+    for (int o = 16; o > 0; o >>= 1) { part += __shfl_xor_sync(0xffffffffu, part, o); pm = max(pm, __shfl_xor_sync(0xffffffffu, pm, o)); }
+    if (lane == 0 && part) { atomicAdd(&s_sum, part); atomicMax(&s_max, pm); }
+    __syncthreads();
+    if (s_sum == 0ull) {
+        for (int k = tid; k < n; k += 1024) order[k] = k;
+        return;
+    }
+    const float T = (float)s_sum / (float)(n_warps > 0 ? n_warps : 1);
+    const float kmin = -(float)s_max, scale = 255.0f / (T - kmin);
+    auto cls_of = [&](int k) {
+        float due = T;
+        if (band.cnt != nullptr) {
+            const int n_regions = ((band.tiles_y + band.band_rows - 1) / band.band_rows) * band.n_groups;
+            due = T * (float)(region_of_tile(band, (k * kChunk) >> 5) + 1) / (float)n_regions;
+        }
+        float key = due - (float)cost_max[k];
+        int c = (int)((key - kmin) * scale);
+        return c < 0 ? 0 : (c > 255 ? 255 : c);
+    };
+    for (int k = tid; k < n; k += 1024) atomicAdd(&s_hist[cls_of(k)], 1);
+    __syncthreads();
+    if (tid < 32) {                                          // exclusive scan of 256 counts: 8 per lane
+        int v[8], t = 0;
+        for (int q = 0; q < 8; ++q) { v[q] = s_hist[tid * 8 + q]; t += v[q]; }
+        int x = t;
+        for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        int base = x - t;
+        for (int q = 0; q < 8; ++q) { s_hist[tid * 8 + q] = base; base += v[q]; }
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += 1024) order[atomicAdd(&s_hist[cls_of(k)], 1)] = k;
+    __syncthreads();
+    for (int k = tid; k < n; k += 1024) { cost_sum[k] = 0u; cost_max[k] = 0u; }
+}
+
 template <bool TRI, bool STATS, bool AOV>
 __global__ void __launch_bounds__(kPacketThreads)
 k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_prims, const __grid_constant__ CameraBlock cam,
          const __grid_constant__ TileMap tm, int n_work, int spp, uint32_t k0, uint32_t k1, uint32_t sample_offset,
          int resolve, float* __restrict__ d_out, int32_t* __restrict__ d_prim, float* __restrict__ d_t,
-         unsigned int* counter, unsigned long long* d_stats) {
+         unsigned int* counter, unsigned long long* d_stats, const __grid_constant__ BandSignal band,
+         const __grid_constant__ ChunkSchedule sched, unsigned long long* d_block_times) {
     __shared__ uint2 s_stack[kPacketThreads / 32][kStackDepth];
     __shared__ unsigned s_word;
     const int lane = threadIdx.x & 31;
     uint2* stack = s_stack[threadIdx.x >> 5];
     const int n_chunks = (n_work + kChunk - 1) / kChunk;
-    if (threadIdx.x == 0) {
-        const unsigned c = atomicAdd(counter, 1u);
-        s_word = (c < (unsigned)n_chunks ? c : kNoChunk) << 8;
-    }
+    if (threadIdx.x == 0) s_word = take_chunk(counter, n_chunks, sched.order);
     __syncthreads();
     const double inv_w = __ddiv_rn(1.0, (double)tm.width), inv_h = __ddiv_rn(1.0, (double)tm.height);
     const float inv_spp = __fdiv_rn(1.0f, (float)spp);
     Counters cnt = {0, 0, 0};
     unsigned long long rays = 0;
     for (;;) {
-        const int w = chunk_next_block(&s_word, counter, n_chunks, lane);
+        const int w = chunk_next_block(&s_word, counter, n_chunks, sched.order, lane);
         if (w < 0) break;
         if (w >= n_work) continue;
         PixelWork p = decode_work(tm, w, lane);
         const uint32_t pixel = (uint32_t)(p.j * tm.width + p.i);
         float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+        int work = 0;
+        unsigned long long t_start = 0;
+        if (STATS && d_block_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
         for (int s = 0; s < spp; ++s) {
             float jx = 0.5f, jy = 0.5f;
             if (!AOV) {
@@ -293,7 +355,7 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
             }
             Ray r = camera_ray(cam, p.i, p.j, jx, jy, inv_w, inv_h);
             Hit h;
-            packet_intersect<TRI, STATS>(sc, cam_prims, r, p.active, lane, stack, h, cnt);
+            packet_intersect<TRI, STATS>(sc, cam_prims, r, p.active, lane, stack, h, cnt, work);
             if (STATS && p.active) { rays += 1; cnt.segments += 1; }
             if (AOV) {
                 if (p.active) { d_prim[p.out_index] = h.prim; d_t[p.out_index] = h.prim >= 0 ? h.t : 0.0f; }
@@ -312,6 +374,23 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
             float* o = d_out + 3 * (size_t)p.out_index;
             if (resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
             else { o[0] = sr; o[1] = sg; o[2] = sb; }
+        }
+        if (sched.order != nullptr && lane == 0) {
+            atomicAdd(sched.cost_sum + w / kChunk, (unsigned)work);
+            atomicMax(sched.cost_max + w / kChunk, (unsigned)work);
+        }
+        if (STATS && d_block_times && lane == 0) {
+            unsigned long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            d_block_times[2 * (size_t)w] = t_start; d_block_times[2 * (size_t)w + 1] = t_end;
+        }
+        if (!AOV && band.cnt != nullptr) {                   // see BandSignal
+            __threadfence();                                 // release: this block's pixels before the count
+            __syncwarp();
+            if (lane == 0) {
+                const int b = region_of_tile(band, w >> 5);
+                if (atomicAdd(band.cnt + b, 1u) + 1u == (unsigned)region_blocks(band, b)) { __threadfence_system(); band.flags[b] = 1u; }
+            }
         }
     }
     if (STATS) flush_stats(d_stats, rays, cnt);
@@ -387,13 +466,19 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
     int grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);
     int need = (n_work + kChunk - 1) / kChunk;
     if (grid > need) grid = need;
+    if (cfg.sched.order != nullptr) {
+        k_chunk_order<<<1, 1024, 0, cfg.stream>>>(cfg.sched.cost_sum, cfg.sched.cost_max, cfg.sched.order, need,
+                                                  grid * (kPacketThreads / 32), cfg.band);
+    }
     k_packet<TRI, STATS, AOV><<<grid, kPacketThreads, 0, cfg.stream>>>(
         sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
-        d_prim, d_t, cfg.d_work_counter, cfg.d_stats);
+        d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times);
     return cudaGetLastError();
 }
 
 }  // namespace
+
+int packet_chunks(const TileMap& tm) { return (work_items(tm) + kChunk - 1) / kChunk; }
 
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
                                  int32_t* d_prim, float* d_t, const LaunchCfg& cfg) {

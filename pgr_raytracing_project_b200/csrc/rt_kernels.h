@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "rt_device.cuh"
 
 namespace b200rt {
@@ -18,6 +20,44 @@ struct TileMap {
     int compact;                // 0: write frame layout; 1: write [k][tile_h][tile_w][...] layout
 };
 
+// Region-completion signalling of k_packet for rt_render_host's copy/compute overlap: the frame's
+// 32x32 tiles are grouped into rectangular regions (band_rows tile rows x group_cols tile columns,
+// numbered row-major); a warp that finishes a block fences its pixels (gpu scope) and bumps the
+// region's counter, and the warp that completes a region fences system-wide (fences are cumulative)
+// and raises flags[region] in mapped pinned host memory, which the calling host thread polls to start
+// that region's device->host copy (a 2-D copy) while the kernel is still rendering the rest of the
+// frame.  Regions rather than full-width bands, because a frame has a few very slow packets (see
+// ChunkSchedule) and a band that contains one cannot complete before it does; small regions confine
+// the wait to a small share of the bytes.
+struct BandSignal {
+    unsigned int* cnt;               // device, one counter per region, zeroed on the launch stream
+    volatile unsigned int* flags;    // mapped pinned host memory (device pointer), zeroed by the host
+    int tiles_x, tiles_y;            // tile grid of the frame (full-frame tile map only)
+    int band_rows, group_cols;       // region size in tiles
+    int n_groups;                    // regions per band row
+};
+
+__host__ __device__ inline int region_of_tile(const BandSignal& b, int tile) {
+    const int ty = tile / b.tiles_x, tx = tile - ty * b.tiles_x;
+    return (ty / b.band_rows) * b.n_groups + tx / b.group_cols;
+}
+__host__ __device__ inline int region_blocks(const BandSignal& b, int region) {   // 32 8x4 blocks per tile
+    const int by = region / b.n_groups, gx = region - by * b.n_groups;
+    const int rows = min(b.band_rows, b.tiles_y - by * b.band_rows), cols = min(b.group_cols, b.tiles_x - gx * b.group_cols);
+    return rows * cols * 32;
+}
+
+// Cost-aware chunk order of k_packet.  Packets differ in cost by more than 10x (rays that run along a
+// BVH split plane), and a slow packet that starts late is the kernel's tail.  Every frame records the
+// step counts of each chunk; the next frame of the same tile map starts chunks in latest-start-time
+// order (k_chunk_order in rt_kernels.cu).  Pure scheduling: pixels do not depend on it.
+// order == nullptr: raster order, nothing recorded.
+struct ChunkSchedule {
+    int* order;                      // n_chunks entries, written by k_chunk_order, read by k_packet
+    unsigned int* cost_sum;          // n_chunks: sum of the chunk's block costs (last frame in, this frame out)
+    unsigned int* cost_max;          // n_chunks: largest block cost of the chunk
+};
+
 struct LaunchCfg {
     cudaStream_t stream;
     int sm_count;
@@ -26,6 +66,9 @@ struct LaunchCfg {
     int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel, 2 = wavefront,
                                              // 3 = k_packet (camera rays: warp = packet with one shared stack)
     float4* d_cam_prims;                     // per-frame camera-relative triangle records (3 x float4 per slot)
+    BandSignal band;                         // cnt == nullptr: no signalling
+    ChunkSchedule sched;                     // order == nullptr: raster order, no cost recording
+    unsigned long long* d_block_times;       // debug (instrumented k_packet only): [2 * work item] = globaltimer start, end; or nullptr
     int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes
     int leaf_vote;                           // phase voting: leaf step when >= this many lanes hold a leaf
 };
@@ -45,6 +88,7 @@ cudaError_t launch_wavefront(const SceneView& sc, bool is_tri, bool aov, const C
                              int spp, int max_depth, int integrator, uint64_t seed, uint32_t sample_offset, int resolve,
                              float* d_out, int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb,
                              int* n_launches);
+int packet_chunks(const TileMap& tm);      // chunks k_packet cuts this tile map into (ChunkSchedule sizes)
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
                                  int32_t* d_prim, float* d_t, const LaunchCfg& cfg);
 cudaError_t launch_trace_rays(const SceneView& sc, bool is_tri, const float* d_org, const float* d_dir, int64_t n,

@@ -233,6 +233,26 @@ def test_tiles_compose_to_frame(ctx, make, spp, depth):
         assert torch.equal(frame, full)
 
 
+@pytest.mark.parametrize("W,H", [(640, 480), (1000, 333)])
+def test_render_host_matches_device_render(ctx, W, H):
+    """rt_render_host (host buffer; for camera-ray frames the device->host copy of finished bands overlaps
+    the rest of the render) returns exactly the frame rt_render leaves on the device, pinned or pageable."""
+    import torch
+    s = scenes.random_triangles(30_000, seed=21)
+    _setup(ctx, s, W, H)
+    for depth, spp in [(1, 2), (3, 1)]:
+        dev = ctx.render(W, H, spp, depth, seed=77, sample_offset=3).cpu().numpy()
+        pinned = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+        for overlap in (1, 0):
+            ctx.set_option("overlap", overlap)
+            pinned.zero_()
+            ctx.render_host(W, H, spp, depth, seed=77, sample_offset=3, out=pinned.numpy())
+            assert np.array_equal(pinned.numpy(), dev)
+        ctx.set_option("overlap", 1)
+        pageable = ctx.render_host(W, H, spp, depth, seed=77, sample_offset=3)
+        assert np.array_equal(pageable, dev)
+
+
 def test_sample_offset_continues_the_sequence(ctx):
     s = scenes.default_scene()
     W, H = 64, 48
