@@ -9,8 +9,9 @@ Workload (BASELINE.json metric "Mrays/s and ms/frame at 1920x1080", configs[2]):
 camera (0,0,30) -> origin, fov 45, 1920x1080, primary rays: one jittered camera sample per pixel,
 max_depth 1, mean -> sqrt -> clamp into the float32 RGB framebuffer.  A step is one frame.
 At N > 1 the frame is sample-range partitioned: every GPU renders its own 1 spp of the full frame
-(weak scaling: N x 2.07 M rays per step), partial sums are reduced to rank 0 over NCCL/NVLink and
-resolved there -- the reduce and the resolve are inside the timed step.
+(weak scaling: N x 2.07 M rays per step) straight into its plane of rank 0's shared buffer (peer stores
+over NVLink from the render kernel), then a barrier, then rank 0 sums the planes in rank order and
+resolves -- all inside the timed step.
 
 One JSON line on stdout (rank 0).  `value` is device-timed with the scene resident in HBM; `e2e`
 is the same frame through the C-ABI host-buffer call (rt_set_camera + rt_render_host: camera in,
@@ -46,6 +47,16 @@ BYTES_NODE, BYTES_TRI, BYTES_OUT = 32, 48, 12      # per node 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+# The contract is ONE JSON line on stdout.  Libraries print banners there (NCCL's version line, OpenMP
+# notices), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 
 def measured_peaks():
@@ -219,7 +230,7 @@ def reference_arm(args):
         out["reference_v1_sphere_twin"] = v1_sphere_twin()
     except Exception as exc:  # noqa: BLE001
         out["reference_v1_sphere_twin"] = {"unavailable": str(exc)}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -263,7 +274,7 @@ def main():
     cam = scene.camera
     ctx.set_camera(cam.position, cam.target, cam.up, cam.fov)
     nodes, prim_index = ctx.get_bvh()
-    renderer = DistributedRenderer(ctx, rank, world, mode="samples")
+    renderer = DistributedRenderer(ctx, rank, world, mode="peer_samples")
     spp_total = SPP_PER_GPU * world
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=ctx.device)       # 512 MiB > 126 MB L2
 
@@ -281,7 +292,7 @@ def main():
         ctx.reset_stats()
         for k in range(args.steps):
             first = k * spp_total + rank * SPP_PER_GPU
-            ctx.render_sum(W, H, SPP_PER_GPU, MAX_DEPTH, RENDER_SEED, first, out=renderer._buf("part", (H, W, 3)))
+            ctx.render_sum(W, H, SPP_PER_GPU, MAX_DEPTH, RENDER_SEED, first, out=renderer._buf(("part", 0), (H, W, 3)))
         st = ctx.stats()
         ctx.set_option("stats", 0)
         ctx.set_option("kernel", -1)
@@ -300,8 +311,10 @@ def main():
         step(k)
     torch.cuda.synchronize()
 
-    # ---- device-timed region: K steps, CUDA events around each step on the launching stream,
-    # L2 flushed (512 MiB memset) between steps outside the event pairs
+    # ---- device-timed region: K steps, a CUDA-event pair around each step on the launching stream, L2 flushed
+    # (512 MiB memset) between steps outside the event pairs.  At N > 1 a step is: this rank's 1 spp rendered
+    # straight into its plane of rank 0's shared buffer (NVLink peer stores from the render kernel), a one-element
+    # NCCL all-reduce as the barrier, and on rank 0 the ordered plane sum + resolve kernel.
     ctx.reset_stats()
     sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -316,9 +329,9 @@ def main():
     torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = ctx.stats()["launches"]
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=ctx.device)
+    total_ms = torch.tensor([total_ms], dtype=torch.float64, device=ctx.device)
     n_launch = torch.tensor([launches], dtype=torch.float64, device=ctx.device)
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -329,7 +342,7 @@ def main():
 
     # ---- dominant kernel alone (k_render on this rank), for the roofline
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    part = renderer._buf("part", (H, W, 3))
+    part = renderer._buf(("part", 0), (H, W, 3))
     for k in range(args.steps):
         flush.zero_()
         kev[k][0].record()
@@ -396,7 +409,9 @@ def main():
                 "workload": WORKLOAD, "width": W, "height": H, "spp_per_gpu": SPP_PER_GPU, "spp_total": spp_total,
                 "max_depth": MAX_DEPTH, "n_triangles": N_TRIS, "bvh_nodes": int(len(nodes)),
                 "partition": "single GPU" if world == 1 else
-                             f"sample-range: 1 spp of the full frame per GPU, NCCL reduce(SUM) to rank 0 + resolve, inside the step",
+                             "sample-range: 1 spp of the full frame per GPU, written by the render kernel straight into this "
+                             "rank's plane of rank 0's shared buffer (CUDA IPC, NVLink peer stores); barrier = one-element NCCL "
+                             "all-reduce; rank 0 sums the planes in rank order and resolves; all inside the timed step",
                 "l2": "scene+BVH = 64 MB < 126 MB L2, so a 512 MiB memset flushes L2 before every timed step "
                       "(outside the CUDA-event pairs)",
                 "host_bvh_build_plus_upload_s": round(build_s, 2),
@@ -426,7 +441,7 @@ def main():
                 out["cpu_baseline"] = cpu_baseline(scene, nodes, prim_index)
             except Exception as exc:  # noqa: BLE001
                 out["cpu_baseline"] = {"unavailable": str(exc)}
-        print(json.dumps(out), flush=True)
+        emit(out)
     barrier()
     if world > 1:
         dist.destroy_process_group()

@@ -126,12 +126,33 @@ int rt_render(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64
 int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int first_tile,
                     int tile_stride, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
                     int resolve, float* d_out, void* stream);
+/* The same partition written in FRAME layout: rank's tiles of the W x H frame go to their final place in
+ * d_frame (H*W*3 floats), which may be another GPU's frame mapped with rt_frame_open -- the render
+ * kernel's own stores are then the frame exchange (NVLink peer writes), and the G-GPU frame is bit-identical
+ * to the 1-GPU one.  Tiles are dealt out skewed (logical tile L = rank, rank + world, ... sits in tile row
+ * ty = L / tiles_x, column (L % tiles_x + ty) % tiles_x) so that every rank gets a share of every tile
+ * row and every tile column. */
+int rt_render_tiles_frame(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int rank, int world,
+                          int spp, int max_depth, uint64_t seed, uint32_t sample_offset, int resolve,
+                          float* d_frame, void* stream);
+/* Frames shared between the processes of one node (CUDA IPC).  rt_frame_alloc: library-owned device buffer
+ * of `planes` H*W*3 float frames plus its 64-byte handle (send it to the other ranks by any means);
+ * rt_frame_open maps such a buffer into this process (peer access over NVLink); close / free undo them. */
+int rt_frame_alloc(rt_ctx* ctx, int width, int height, int planes, float** d_frame, unsigned char handle[64]);
+int rt_frame_free(rt_ctx* ctx, float* d_frame);
+int rt_frame_open(rt_ctx* ctx, const unsigned char handle[64], float** d_peer_frame);
+int rt_frame_close(rt_ctx* ctx, float* d_peer_frame);
 /* Full frame, raw radiance sums (no mean / gamma / clamp): the per-rank partial of a sample-range
  * partition; sum the partials (e.g. ncclReduce) and finish with rt_resolve. */
 int rt_render_sum(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed,
                   uint32_t sample_offset, float* d_out, void* stream);
 /* mean over spp_total -> sqrt gamma -> clamp [0,1] (cpp_raytracer/raytracer_core.cpp:398-409). */
 int rt_resolve(rt_ctx* ctx, const float* d_sum, float* d_out, int64_t n_floats, int spp_total, void* stream);
+/* Sample-range partition with the exchange done by the render kernels themselves: rank g renders
+ * rt_render_sum straight into plane g of the display rank's shared buffer (rt_frame_alloc / rt_frame_open);
+ * after a barrier the display rank sums the planes in plane order (deterministic) and resolves. */
+int rt_resolve_planes(rt_ctx* ctx, const float* d_planes, int n_planes, int64_t plane_stride_floats, float* d_out,
+                      int64_t n_floats, int spp_total, void* stream);
 /* Scatter gathered compact tile buffers [rank][k][tile_h][tile_w][3] back into a H*W*3 frame. */
 int rt_untile(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int n_ranks,
               const float* d_tiles, float* d_frame, void* stream);

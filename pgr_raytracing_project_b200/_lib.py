@@ -14,7 +14,8 @@ SYMBOLS = [
     "rt_set_background", "rt_build_bvh", "rt_get_bvh", "rt_set_bvh", "rt_set_camera", "rt_get_camera_block",
     "rt_trace_primary", "rt_trace_rays", "rt_select_object", "rt_render", "rt_render_tiles", "rt_untile",
     "rt_render_host", "rt_accumulate", "rt_tonemap_u8", "rt_set_option", "rt_get_option", "rt_get_stats",
-    "rt_reset_stats", "rt_build_bvh_host", "rt_render_sum", "rt_resolve",
+    "rt_reset_stats", "rt_build_bvh_host", "rt_render_sum", "rt_resolve", "rt_render_tiles_frame", "rt_frame_alloc",
+    "rt_frame_free", "rt_frame_open", "rt_frame_close", "rt_resolve_planes",
 ]
 
 
@@ -68,6 +69,12 @@ def load():
         "rt_resolve": (ci, [vp, vp, vp, i64, ci, vp]),
         "rt_render_tiles": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, u64, u32, ci, vp, vp]),
         "rt_untile": (ci, [vp, ci, ci, ci, ci, ci, vp, vp, vp]),
+        "rt_render_tiles_frame": (ci, [vp, ci, ci, ci, ci, ci, ci, ci, ci, u64, u32, ci, vp, vp]),
+        "rt_frame_alloc": (ci, [vp, ci, ci, ci, C.POINTER(vp), C.c_char_p]),
+        "rt_resolve_planes": (ci, [vp, vp, ci, i64, vp, i64, ci, vp]),
+        "rt_frame_free": (ci, [vp, vp]),
+        "rt_frame_open": (ci, [vp, C.c_char_p, C.POINTER(vp)]),
+        "rt_frame_close": (ci, [vp, vp]),
         "rt_render_host": (ci, [vp, ci, ci, ci, ci, u64, u32, vp]),
         "rt_accumulate": (ci, [vp, vp, vp, i64, ci, ci, vp]),
         "rt_tonemap_u8": (ci, [vp, vp, vp, i64, C.c_float, vp]),

@@ -43,6 +43,17 @@ def build_bvh_host(prims: np.ndarray, is_triangles: bool):
     return nodes[:cnt.value].copy(), prim_index
 
 
+class _RawCudaArray:
+    """float32 device memory owned by libb200rt, exposed to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+def _tensor_from_pointer(ptr: int, shape, device_index: int) -> torch.Tensor:
+    return torch.as_tensor(_RawCudaArray(ptr, shape), device=torch.device("cuda", device_index))
+
+
 class RenderContext:
     """One rendering context on one GPU (rt_create .. rt_destroy)."""
 
@@ -174,12 +185,14 @@ class RenderContext:
         return out
 
     def render_sum(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Raw radiance sums of samples [sample_offset, sample_offset + spp) (sample-range partials)."""
+                   out=None):
+        """Raw radiance sums of samples [sample_offset, sample_offset + spp) (sample-range partials).
+        out: a (H,W,3) CUDA tensor, or a raw device pointer (int) such as a plane of a peer-mapped buffer."""
         if out is None:
             out = torch.empty((height, width, 3), dtype=torch.float32, device=self.device)
+        ptr = out if isinstance(out, int) else out.data_ptr()
         self._ck(self.L.rt_render_sum(self.h, width, height, spp, max_depth, C.c_uint64(seed), C.c_uint32(sample_offset),
-                                      out.data_ptr(), self._stream()))
+                                      ptr, self._stream()))
         return out
 
     def resolve(self, summed: torch.Tensor, spp_total: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -201,6 +214,42 @@ class RenderContext:
                                         C.c_uint64(seed), C.c_uint32(sample_offset), int(resolve), out.data_ptr(),
                                         self._stream()))
         return out
+
+    def render_tiles_frame(self, width: int, height: int, tile_w: int, tile_h: int, rank: int, world: int, spp: int,
+                           max_depth: int, seed: int = 0, sample_offset: int = 0, resolve: bool = True, frame=None):
+        """rank's (skew-interleaved) tiles written in place into `frame`: a (H,W,3) float32 CUDA tensor or a raw
+        device pointer (int), e.g. another GPU's frame mapped with frame_open()."""
+        ptr = frame if isinstance(frame, int) else frame.data_ptr()
+        self._ck(self.L.rt_render_tiles_frame(self.h, width, height, tile_w, tile_h, rank, world, spp, max_depth,
+                                              C.c_uint64(seed), C.c_uint32(sample_offset), int(resolve), ptr, self._stream()))
+
+    # ------------------------------------------------------------------ frames shared across processes (CUDA IPC)
+    def frame_alloc(self, width: int, height: int, planes: int = 1):
+        """-> (device pointer, 64-byte handle, torch view (planes,H,W,3)) of a library-owned shareable buffer."""
+        p = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self._ck(self.L.rt_frame_alloc(self.h, width, height, planes, C.byref(p), handle))
+        return int(p.value), handle.raw, _tensor_from_pointer(int(p.value), (planes, height, width, 3), self.device_index)
+
+    def resolve_planes(self, planes: torch.Tensor, spp_total: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """planes: (P,H,W,3) raw radiance sums -> resolved (H,W,3): ordered sum over P, mean, sqrt, clamp."""
+        if out is None:
+            out = torch.empty(planes.shape[1:], dtype=torch.float32, device=self.device)
+        n = out.numel()
+        self._ck(self.L.rt_resolve_planes(self.h, planes.data_ptr(), planes.shape[0], n, out.data_ptr(), n, int(spp_total),
+                                          self._stream()))
+        return out
+
+    def frame_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.rt_frame_open(self.h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return int(p.value)
+
+    def frame_close(self, ptr: int):
+        self._ck(self.L.rt_frame_close(self.h, C.c_void_p(ptr)))
+
+    def frame_free(self, ptr: int):
+        self._ck(self.L.rt_frame_free(self.h, C.c_void_p(ptr)))
 
     def untile(self, width: int, height: int, tile_w: int, tile_h: int, n_ranks: int, tiles: torch.Tensor,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -276,7 +276,7 @@ int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm) {
         ctx->chunk_cap = n_chunks;
     }
     long long key = ((((long long)tm.width * 65537 + tm.height) * 257 + tm.tile_w) * 257 + tm.tile_h) * 1031 + tm.first_tile;
-    key = key * 1031 + tm.tile_stride + 7919LL * tm.compact + 104729LL * tm.n_local_tiles;
+    key = key * 1031 + tm.tile_stride + 7919LL * tm.compact + 104729LL * tm.n_local_tiles + 15485863LL * tm.skew;
     if (key != ctx->chunk_key) {
         CK(cudaMemsetAsync(ctx->d_chunk_cost, 0, (size_t)ctx->chunk_cap * 2 * sizeof(unsigned int), cfg.stream));
         ctx->chunk_key = key;
@@ -297,7 +297,7 @@ TileMap full_frame_map(int width, int height) {
     tm.tiles_x = (width + 31) / 32;
     tm.n_tiles = tm.tiles_x * ((height + 31) / 32);
     tm.first_tile = 0; tm.tile_stride = 1; tm.n_local_tiles = tm.n_tiles;
-    tm.compact = 0;
+    tm.compact = 0; tm.skew = 0;
     return tm;
 }
 
@@ -548,8 +548,8 @@ int rt_select_object(rt_ctx* ctx, double x, double y, int width, int height, int
     return 0;
 }
 
-int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int first_tile, int tile_stride, int spp,
-                    int max_depth, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out, void* stream) {
+static int render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int first_tile, int tile_stride, int spp,
+                        int max_depth, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out, void* stream, int layout) {
     if (!ctx) return 1;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (int rc = check_frame(ctx, width, height)) return rc;
@@ -565,7 +565,7 @@ int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, 
     tm.n_tiles = tm.tiles_x * ((height + tile_h - 1) / tile_h);
     tm.first_tile = first_tile; tm.tile_stride = tile_stride;
     tm.n_local_tiles = first_tile < tm.n_tiles ? (tm.n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
-    tm.compact = 1;
+    tm.compact = layout == 0 ? 1 : 0; tm.skew = layout == 0 ? 0 : 1;
     if (pick_kernel(ctx, max_depth) == 2 && tm.n_local_tiles) {
         if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
         int nl = 0;
@@ -579,6 +579,67 @@ int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, 
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
     if (tm.n_local_tiles) ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
+    return 0;
+}
+
+int rt_render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int first_tile, int tile_stride, int spp,
+                    int max_depth, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out, void* stream) {
+    return render_tiles(ctx, width, height, tile_w, tile_h, first_tile, tile_stride, spp, max_depth, seed, sample_offset, resolve,
+                        d_out, stream, 0);
+}
+
+int rt_render_tiles_frame(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int rank, int world, int spp,
+                          int max_depth, uint64_t seed, uint32_t sample_offset, int resolve, float* d_frame, void* stream) {
+    if (ctx && (rank < 0 || world <= 0 || rank >= world)) return fail(ctx, "rt_render_tiles_frame: bad rank / world");
+    return render_tiles(ctx, width, height, tile_w, tile_h, rank, world, spp, max_depth, seed, sample_offset, resolve, d_frame,
+                        stream, 1);
+}
+
+// ---- frames shared between the processes of one node (CUDA IPC): the display rank allocates, the others map
+// it and render their tiles straight into it over NVLink (rt_render_tiles_frame), so the frame exchange is
+// the render kernel's own stores.
+int rt_frame_alloc(rt_ctx* ctx, int width, int height, int planes, float** d_frame, unsigned char handle[64]) {
+    if (!ctx || !d_frame || !handle) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (int rc = check_frame(ctx, width, height)) return rc;
+    if (planes < 1 || planes > 64) return fail(ctx, "rt_frame_alloc: planes must be in 1..64");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard g(ctx->device);
+    float* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)planes * width * height * 3 * sizeof(float)));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(ctx, "cudaIpcGetMemHandle", e); }
+    std::memcpy(handle, &h, 64);
+    *d_frame = p;
+    return 0;
+}
+
+int rt_frame_free(rt_ctx* ctx, float* d_frame) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaFree(d_frame));
+    return 0;
+}
+
+int rt_frame_open(rt_ctx* ctx, const unsigned char handle[64], float** d_peer_frame) {
+    if (!ctx || !handle || !d_peer_frame) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_peer_frame = static_cast<float*>(p);
+    return 0;
+}
+
+int rt_frame_close(rt_ctx* ctx, float* d_peer_frame) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaIpcCloseMemHandle(d_peer_frame));
     return 0;
 }
 
@@ -626,6 +687,18 @@ int rt_resolve(rt_ctx* ctx, const float* d_sum, float* d_out, int64_t n, int spp
     if (n < 0 || spp_total <= 0 || (n > 0 && (!d_sum || !d_out))) return fail(ctx, "rt_resolve: bad arguments");
     DeviceGuard g(ctx->device);
     CK(launch_resolve(d_sum, d_out, n, spp_total, (cudaStream_t)stream));
+    if (n) ctx->launches += 1;
+    return 0;
+}
+
+int rt_resolve_planes(rt_ctx* ctx, const float* d_planes, int n_planes, int64_t plane_stride, float* d_out, int64_t n,
+                      int spp_total, void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || n_planes < 1 || plane_stride < n || spp_total <= 0 || (n > 0 && (!d_planes || !d_out)))
+        return fail(ctx, "rt_resolve_planes: bad arguments");
+    DeviceGuard g(ctx->device);
+    CK(launch_resolve_planes(d_planes, n_planes, plane_stride, d_out, n, spp_total, (cudaStream_t)stream));
     if (n) ctx->launches += 1;
     return 0;
 }

@@ -17,6 +17,7 @@ __device__ __forceinline__ PixelWork decode_work(const TileMap& tm, int w, int l
     int sy = sub / bx, sx = sub - sy * bx;
     int tile = tm.first_tile + k * tm.tile_stride;
     int ty = tile / tm.tiles_x, tx = tile - ty * tm.tiles_x;
+    if (tm.skew) tx = (tx + tm.skew * ty) % tm.tiles_x;
     int lx = (sx << 3) + (lane & 7), ly = (sy << 2) + (lane >> 3);
     PixelWork p;
     p.i = tx * tm.tile_w + lx;

@@ -414,6 +414,16 @@ __global__ void k_resolve(const float* __restrict__ sum, float* __restrict__ out
         out[k] = resolve1(sum[k], inv_spp);
 }
 
+// Sum of n_planes partial-sum frames IN PLANE ORDER ((p0 + p1) + p2 ...: deterministic), then resolve.
+__global__ void k_resolve_planes(const float* __restrict__ planes, int n_planes, int64_t plane_stride, float* __restrict__ out,
+                                 int64_t n, float inv_spp) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        float s = planes[k];
+        for (int p = 1; p < n_planes; ++p) s = __fadd_rn(s, planes[(int64_t)p * plane_stride + k]);
+        out[k] = resolve1(s, inv_spp);
+    }
+}
+
 // interaction.py:1311-1325 in float32: accum*w_old + batch*w_new, each product rounded.
 __global__ void k_accumulate(const float* __restrict__ batch, float* __restrict__ accum, int64_t n, float w_old,
                              float w_new, int first) {
@@ -581,6 +591,13 @@ cudaError_t launch_untile(int width, int height, int tile_w, int tile_h, int n_r
 cudaError_t launch_resolve(const float* d_sum, float* d_out, int64_t n, int spp_total, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     k_resolve<<<elementwise_grid(n), 256, 0, stream>>>(d_sum, d_out, n, 1.0f / (float)spp_total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_resolve_planes(const float* d_planes, int n_planes, int64_t plane_stride, float* d_out, int64_t n,
+                                  int spp_total, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_resolve_planes<<<elementwise_grid(n), 256, 0, stream>>>(d_planes, n_planes, plane_stride, d_out, n, 1.0f / (float)spp_total);
     return cudaGetLastError();
 }
 

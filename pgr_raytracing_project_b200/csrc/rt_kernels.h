@@ -18,6 +18,8 @@ struct TileMap {
     int tiles_x, n_tiles;
     int first_tile, tile_stride, n_local_tiles;
     int compact;                // 0: write frame layout; 1: write [k][tile_h][tile_w][...] layout
+    int skew;                   // logical tile L = row ty, column (L % tiles_x + skew * ty) % tiles_x: with skew != 0 a
+                                // rank's tiles L = rank, rank + world, ... hit every tile row AND every tile column
 };
 
 // Region-completion signalling of k_packet for rt_render_host's copy/compute overlap: the frame's
@@ -99,6 +101,8 @@ cudaError_t launch_render(const SceneView& sc, bool is_tri, const CameraBlock& c
 cudaError_t launch_untile(int width, int height, int tile_w, int tile_h, int n_ranks, const float* d_tiles,
                           float* d_frame, cudaStream_t stream);
 cudaError_t launch_resolve(const float* d_sum, float* d_out, int64_t n, int spp_total, cudaStream_t stream);
+cudaError_t launch_resolve_planes(const float* d_planes, int n_planes, int64_t plane_stride, float* d_out, int64_t n,
+                                  int spp_total, cudaStream_t stream);
 cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, int n_old, int n_batch,
                               cudaStream_t stream);
 cudaError_t launch_tonemap_u8(const float* d_accum, uint8_t* d_rgb8, int64_t n, float exposure, cudaStream_t stream);

@@ -14,6 +14,18 @@ the data path -- only the final framebuffer exchange over NCCL/NVLink:
                 millisecond of GPU time) from being launch-latency bound at 8 GPUs; the float sum
                 order differs from the 1-GPU one (not bit-identical, same expectation).
 
+* ``peer``    : the tile partition with the exchange fused into the render kernel: the display rank
+                (0) owns the frame and shares it with the other processes (CUDA IPC); every rank's
+                kernel stores its resolved pixels straight into that frame -- its own HBM or, over
+                NVLink peer writes, rank 0's -- so the transfer overlaps the tracing pixel by pixel
+                and nothing is left at the end of the frame but a barrier.  Tiles are dealt out
+                skewed (`skewed_tiles_of`) so that every rank gets part of every tile row and
+                column.  Bit-identical to the 1-GPU frame like ``tiles``.
+
+* ``peer_samples`` : the sample-range partition with the same fused exchange: rank g renders its
+                raw sums straight into plane g of rank 0's shared buffer; after the barrier rank 0
+                adds the planes in rank order (deterministic) and resolves in one kernel.
+
 The partition arithmetic below is pure Python and is exercised on CPU with gloo in
 tests/test_multigpu_cpu.py; the GPU driver (`DistributedRenderer`) only adds the kernels.
 """
@@ -71,6 +83,16 @@ class TilePlan:
         return out
 
 
+def skewed_tiles_of(plan: "TilePlan", rank: int) -> List[int]:
+    """Row-major tile numbers of `rank` under the skewed deal of rt_render_tiles_frame: logical tile
+    L = rank, rank + world, ... sits in tile row ty = L // tiles_x, column (L % tiles_x + ty) % tiles_x."""
+    out = []
+    for L in range(rank, plan.n_tiles, plan.world):
+        ty, tx = divmod(L, plan.tiles_x)
+        out.append(ty * plan.tiles_x + (tx + ty) % plan.tiles_x)
+    return out
+
+
 def sample_range(spp: int, rank: int, world: int) -> Tuple[int, int]:
     """(first sample, count) of `rank` in a sample-range partition of `spp` samples."""
     base, rem = divmod(spp, world)
@@ -82,9 +104,10 @@ class DistributedRenderer:
     """Tile- or sample-sharded rendering across the ranks of a torch.distributed group (NCCL)."""
 
     def __init__(self, ctx, rank: int, world: int, mode: str = "tiles", tile: Tuple[int, int] = (32, 32), group=None):
-        assert mode in ("tiles", "samples")
+        assert mode in ("tiles", "samples", "peer", "peer_samples")
         self.ctx, self.rank, self.world, self.mode, self.tile, self.group = ctx, rank, world, mode, tile, group
         self._bufs = {}
+        self._shared = {}          # (W, H, slot) -> (pointer, torch view or None, owner?)
 
     def _buf(self, key, shape):
         import torch
@@ -94,29 +117,93 @@ class DistributedRenderer:
             self._bufs[key] = b
         return b
 
-    def render(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0):
-        """tiles: the resolved frame on every rank.  samples: the resolved frame on rank 0 (None elsewhere)."""
+    def _shared_frame(self, width: int, height: int, slot: int):
+        """Rank 0's frame for (W, H, slot), mapped into every process.  Collective on first use."""
+        import torch
         import torch.distributed as dist
+        key = (width, height, slot)
+        if key not in self._shared:
+            h = torch.zeros(64, dtype=torch.uint8, device=self.ctx.device)
+            view = None
+            if self.rank == 0:
+                ptr, handle, view = self.ctx.frame_alloc(width, height, self.world if self.mode == "peer_samples" else 1)
+                h.copy_(torch.frombuffer(bytearray(handle), dtype=torch.uint8))
+            dist.broadcast(h, src=0, group=self.group)
+            if self.rank != 0:
+                ptr = self.ctx.frame_open(bytes(h.cpu().numpy().tobytes()))
+            self._shared[key] = (ptr, view)
+            self._token = torch.zeros(1, device=self.ctx.device)
+        return self._shared[key]
+
+    def close(self):
+        for (ptr, view) in self._shared.values():
+            (self.ctx.frame_free if self.rank == 0 else self.ctx.frame_close)(ptr)
+        self._shared = {}
+
+    def render(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0, slot: int = 0):
+        """tiles: the resolved frame on every rank.  samples: the resolved frame on rank 0 (None elsewhere)."""
+        local = self.render_local(width, height, spp, max_depth, seed, sample_offset, slot)
+        return self.combine(local, width, height, spp, slot)
+
+    def render_local(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0,
+                     slot: int = 0):
+        """This rank's share of the frame, no communication (kernels on the current stream).  `slot` selects
+        one of several buffer sets so that frames can be pipelined: render_local(slot k+1) may run while
+        combine(slot k) is still exchanging on another stream."""
         ctx = self.ctx
         if self.world == 1:
-            return ctx.render(width, height, spp, max_depth, seed, sample_offset, out=self._buf("frame", (height, width, 3)))
+            return ctx.render(width, height, spp, max_depth, seed, sample_offset, out=self._buf(("frame", slot), (height, width, 3)))
+        if self.mode == "peer":
+            ptr, view = self._shared_frame(width, height, slot)
+            ctx.render_tiles_frame(width, height, self.tile[0], self.tile[1], self.rank, self.world, spp, max_depth, seed,
+                                   sample_offset, True, frame=ptr)
+            return None if view is None else view[0]
+        if self.mode == "peer_samples":
+            ptr, view = self._shared_frame(width, height, slot)
+            first, count = sample_range(spp, self.rank, self.world)
+            assert count > 0, "peer_samples needs at least one sample per rank"
+            ctx.render_sum(width, height, count, max_depth, seed, sample_offset + first,
+                           out=ptr + self.rank * height * width * 3 * 4)
+            return view
         if self.mode == "tiles":
             plan = TilePlan(width, height, self.tile[0], self.tile[1], self.world)
-            mine = self._buf("mine", plan.compact_shape())
+            mine = self._buf(("mine", slot), plan.compact_shape())
             ctx.render_tiles(width, height, plan.tile_w, plan.tile_h, self.rank, self.world, spp, max_depth, seed,
                              sample_offset, True, out=mine)
-            cs = plan.compact_shape()
-            gathered = self._buf("gathered", (self.world * cs[0],) + cs[1:])
-            dist.all_gather_into_tensor(gathered, mine, group=self.group)
-            return ctx.untile(width, height, plan.tile_w, plan.tile_h, self.world, gathered,
-                              out=self._buf("frame", (height, width, 3)))
+            return mine
         first, count = sample_range(spp, self.rank, self.world)
-        part = self._buf("part", (height, width, 3))
+        part = self._buf(("part", slot), (height, width, 3))
         if count > 0:
             ctx.render_sum(width, height, count, max_depth, seed, sample_offset + first, out=part)
         else:
             part.zero_()
-        dist.reduce(part, dst=0, op=dist.ReduceOp.SUM, group=self.group)
+        return part
+
+    def combine(self, local, width: int, height: int, spp: int, slot: int = 0):
+        """The frame exchange of render() for a buffer produced by render_local() (collective + the
+        untile / resolve kernel, all ordered on the current stream)."""
+        import torch.distributed as dist
+        ctx = self.ctx
+        if self.world == 1:
+            return local
+        if self.mode == "peer":
+            # the pixels are already in rank 0's frame; what remains is "every rank's kernel has finished":
+            # a one-element all-reduce, stream-ordered after the render kernel on every rank
+            dist.all_reduce(self._token, group=self.group)
+            return local
+        if self.mode == "peer_samples":
+            dist.all_reduce(self._token, group=self.group)
+            if self.rank != 0:
+                return None
+            return ctx.resolve_planes(local, spp, out=self._buf(("frame", slot), (height, width, 3)))
+        if self.mode == "tiles":
+            plan = TilePlan(width, height, self.tile[0], self.tile[1], self.world)
+            cs = plan.compact_shape()
+            gathered = self._buf(("gathered", slot), (self.world * cs[0],) + cs[1:])
+            dist.all_gather_into_tensor(gathered, local, group=self.group)
+            return ctx.untile(width, height, plan.tile_w, plan.tile_h, self.world, gathered,
+                              out=self._buf(("frame", slot), (height, width, 3)))
+        dist.reduce(local, dst=0, op=dist.ReduceOp.SUM, group=self.group)
         if self.rank != 0:
             return None
-        return ctx.resolve(part, spp, out=self._buf("frame", (height, width, 3)))
+        return ctx.resolve(local, spp, out=self._buf(("frame", slot), (height, width, 3)))

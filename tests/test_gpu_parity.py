@@ -233,6 +233,38 @@ def test_tiles_compose_to_frame(ctx, make, spp, depth):
         assert torch.equal(frame, full)
 
 
+@pytest.mark.parametrize("make,spp,depth", [
+    (lambda: scenes.default_scene(), 3, 4),
+    (lambda: scenes.random_triangles(5_000, seed=4), 2, 1),
+])
+def test_frame_layout_tiles_compose_in_place(ctx, make, spp, depth):
+    """The peer-memory partition (rt_render_tiles_frame): every rank's skew-dealt tiles written in place into one
+    frame == the one-shot render, bit for bit.  (One device stands in for all ranks here; the cross-process
+    CUDA-IPC mapping is exercised by tests/test_multigpu_gpu.py on a multi-GPU box.)"""
+    import torch
+    s = make()
+    W, H = 200, 120
+    _setup(ctx, s, W, H)
+    full = ctx.render(W, H, spp, depth, seed=9)
+    for n_ranks, tw, th in [(2, 32, 32), (3, 64, 8), (8, 32, 32)]:
+        frame = torch.full((H, W, 3), -1.0, device=full.device)
+        for r in range(n_ranks):
+            ctx.render_tiles_frame(W, H, tw, th, r, n_ranks, spp, depth, seed=9, frame=frame)
+        assert torch.equal(frame, full)
+
+
+def test_resolve_planes_is_the_ordered_sum(ctx):
+    import torch
+    rng = np.random.default_rng(3)
+    planes = rng.random((5, 40, 56, 3)).astype(np.float32) * 3
+    got = ctx.resolve_planes(torch.from_numpy(planes).to(ctx.device), 5).cpu().numpy()
+    acc = planes[0].copy()
+    for p in planes[1:]:
+        acc = acc + p
+    want = np.clip(np.sqrt(acc * np.float32(1.0 / 5)), 0.0, 1.0)
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("W,H", [(640, 480), (1000, 333)])
 def test_render_host_matches_device_render(ctx, W, H):
     """rt_render_host (host buffer; for camera-ray frames the device->host copy of finished bands overlaps

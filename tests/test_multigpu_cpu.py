@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-from pgr_raytracing_project_b200.multigpu import TilePlan, sample_range  # noqa: E402
+from pgr_raytracing_project_b200.multigpu import TilePlan, sample_range, skewed_tiles_of  # noqa: E402
 
 
 def test_tile_plan_covers_frame_once():
@@ -31,6 +31,21 @@ def test_tile_plan_covers_frame_once():
         assert (cover == 1).all() and sorted(owners) == list(range(plan.n_tiles))
         counts = [len(plan.tiles_of(r)) for r in range(world)]
         assert max(counts) - min(counts) <= 1
+
+
+def test_skewed_deal_covers_frame_once_and_spreads_rows_and_columns():
+    """The deal of rt_render_tiles_frame (peer mode): a permutation of the tiles, balanced to within one tile,
+    and -- unlike the plain interleave -- every rank gets a share of every tile column and every tile row."""
+    for (W, H, world) in [(1920, 1080, 8), (1920, 1080, 4), (3840, 2160, 8), (200, 120, 3), (33, 31, 5), (640, 480, 2)]:
+        plan = TilePlan(W, H, 32, 32, world)
+        per_rank = [skewed_tiles_of(plan, r) for r in range(world)]
+        assert sorted(sum(per_rank, [])) == list(range(plan.n_tiles))
+        counts = [len(t) for t in per_rank]
+        assert max(counts) - min(counts) <= 1
+        if plan.tiles_x >= 2 * world and plan.tiles_y >= 2 * world:
+            for tiles in per_rank:
+                assert {t % plan.tiles_x for t in tiles} == set(range(plan.tiles_x))
+                assert {t // plan.tiles_x for t in tiles} == set(range(plan.tiles_y))
 
 
 def test_sample_ranges_partition_spp():
@@ -71,6 +86,30 @@ def _worker(rank, world, port, mode, out_dir):
         gathered = torch.zeros((world * cs[0],) + cs[1:])
         dist.all_gather_into_tensor(gathered, torch.from_numpy(mine))
         frame = plan.untile_numpy(gathered.numpy())
+    elif mode == "peer":
+        # every rank writes its skew-dealt tiles in place into rank 0's frame (here: gathered full frames,
+        # each rank's contribution masked to its own tiles)
+        plan = TilePlan(W, H, 32, 32, world)
+        mine = np.zeros((H, W, 3), dtype=np.float32)
+        for tile in skewed_tiles_of(plan, rank):
+            x0, y0, w, h = plan.tile_rect(tile)
+            img, _ = o.render(W, H, spp, depth, seed=seed, rect=(x0, y0, w, h))
+            mine[y0:y0 + h, x0:x0 + w] = img
+        t = torch.from_numpy(mine)
+        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)          # disjoint supports: the sum is a placement
+        frame = t.numpy()
+    elif mode == "peer_samples":
+        # rank g's raw sums = plane g on rank 0; rank 0 adds the planes in rank order, then resolves
+        first, count = sample_range(spp, rank, world)
+        part, _ = o.render(W, H, count, depth, seed=seed, sample_offset=first, resolve=False)
+        planes = [torch.zeros((H, W, 3)) for _ in range(world)] if rank == 0 else None
+        dist.gather(torch.from_numpy(part), planes, dst=0)
+        frame = None
+        if rank == 0:
+            acc = planes[0].numpy().copy()
+            for p in planes[1:]:
+                acc = acc + p.numpy()
+            frame = np.clip(np.sqrt(acc * np.float32(1.0 / spp)), 0.0, 1.0)
     else:
         first, count = sample_range(spp, rank, world)
         part, _ = o.render(W, H, count, depth, seed=seed, sample_offset=first, resolve=False)
@@ -85,12 +124,12 @@ def _worker(rank, world, port, mode, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["tiles", "samples"])
+@pytest.mark.parametrize("mode", ["tiles", "samples", "peer", "peer_samples"])
 def test_world2_gloo_matches_single_process(tmp_path, mode):
     mp.spawn(_worker, args=(2, _free_port(), mode, str(tmp_path)), nprocs=2, join=True)
     frame = np.load(tmp_path / f"{mode}_frame.npy")
     full = np.load(tmp_path / f"{mode}_full.npy")
-    if mode == "tiles":
+    if mode in ("tiles", "peer"):
         assert np.array_equal(frame, full)          # bit-identical to the 1-process frame
     else:
         np.testing.assert_allclose(frame, full, atol=2e-6)   # float re-association of the sample sum
