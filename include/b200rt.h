@@ -177,7 +177,9 @@ int rt_tonemap_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
  * scene size and max_depth), 0 = persistent path kernel with lane-level continuation, 1 = simple
  * one-pixel-per-thread megakernel, 2 = wavefront (generate / trace / shade / accumulate kernels over
  * compacted ray queues), 3 = camera-ray packets (max_depth 1 and the primary-hit query: a warp walks
- * the BVH as one 8x4-pixel packet; falls back to 0 for max_depth > 1) -- all give bit-identical results; "refill" 1..32 = share (in 32nds)
+ * the BVH as one 8x4-pixel packet; falls back to 0 for max_depth > 1), 4 = wavefront whose bounce 0 (the
+ * coherent camera rays) is generated and traced by packets (falls back to 3 for max_depth 1) -- all give
+ * bit-identical results; "refill" 1..32 = share (in 32nds)
  * of a warp's traversing lanes below which it leaves the traversal loop to shade / refill (default
  * 8); "leaf_vote" 1..32 = lanes holding a leaf at which the warp runs the leaf step (default 8);
  * "overlap" 0/1 = rt_render_host copies finished bands of a camera-ray frame to the host while the

@@ -56,6 +56,14 @@ struct rt_ctx {
     // options
     int integrator = 0, stats = 0, kernel = -1, refill = 8, leaf_vote = 8;
     int kernel_used = -1;                    // variant picked by the most recent tracing launch
+    // auto choice for multi-bounce renders of tiny scenes (<= 64 primitives): which of the lock-step megakernel
+    // (open scenes, short paths: the reference's default scene) and the wavefront (closed scenes, long paths: a
+    // Cornell box) wins depends on the scene, so the first two such renders after a scene upload are timed, one
+    // with each (all variants give the same pixels), and the faster one is kept
+    int tune_state = 0;                      // 0, 1: candidate to time next; 2: decided
+    int tune_pending = -1;                   // candidate whose timing events are in flight
+    double tune_pending_samples = 0, tune_rate[2] = {0, 0};
+    cudaEvent_t tune_ev0 = nullptr, tune_ev1 = nullptr;
 
     unsigned int* d_work_counter = nullptr;
     unsigned long long* d_stats = nullptr;   // rays, segments, node_records, prim_tests
@@ -237,20 +245,48 @@ SceneView scene_view(const rt_ctx* c) {
 
 // Kernel choice when option "kernel" is -1 (auto), from B200 measurements (DESIGN.md "Kernel choice"):
 // tiny scenes are shading-bound and favour the lock-step megakernel; multi-bounce paths favour the
-// wavefront queues; single-segment (camera-ray) work favours the packet kernel.
+// wavefront queues, with the coherent bounce 0 walked by packets; single-segment (camera-ray) work favours
+// the packet kernel.
 int pick_kernel(const rt_ctx* c, int max_depth) {
-    if (c->kernel >= 0) return (c->kernel == 3 && max_depth != 1) ? 0 : c->kernel;
+    if (c->kernel >= 0) {
+        if (c->kernel == 3 && max_depth != 1) return 0;        // packets handle camera rays only
+        if (c->kernel == 4 && max_depth == 1) return 3;
+        return c->kernel;
+    }
     if (c->n <= 64) return 1;
-    return max_depth >= 2 ? 2 : 3;
+    return max_depth >= 2 ? 4 : 3;
 }
+bool is_wavefront(int variant) { return variant == 2 || variant == 4; }
 
-LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1) {
+constexpr int kTuneCandidates[2] = {1, 2};
+bool tunes(const rt_ctx* c, int max_depth) { return c->kernel < 0 && c->n > 0 && c->n <= 64 && max_depth >= 2; }
+
+// Before a tuned render: collect the timing of the previous one, then say which variant runs now.
+int tune_begin(rt_ctx* c, cudaStream_t stream, double samples) {
+    if (!c->tune_ev0) { cudaEventCreate(&c->tune_ev0); cudaEventCreate(&c->tune_ev1); }
+    if (c->tune_pending >= 0) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(c->tune_ev1) == cudaSuccess && cudaEventElapsedTime(&ms, c->tune_ev0, c->tune_ev1) == cudaSuccess) {
+            c->tune_rate[c->tune_pending] = ms / c->tune_pending_samples;
+            c->tune_state = c->tune_pending + 1;
+        }
+        c->tune_pending = -1;
+    }
+    if (c->tune_state >= 2) return kTuneCandidates[c->tune_rate[1] < c->tune_rate[0] ? 1 : 0];
+    c->tune_pending = c->tune_state;
+    c->tune_pending_samples = samples;
+    cudaEventRecord(c->tune_ev0, stream);
+    return kTuneCandidates[c->tune_state];
+}
+void tune_end(rt_ctx* c, cudaStream_t stream) { if (c->tune_pending >= 0) cudaEventRecord(c->tune_ev1, stream); }
+
+LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -1) {
     LaunchCfg cfg;
     cfg.stream = (cudaStream_t)stream;
     cfg.sm_count = c->sm_count;
     cfg.d_work_counter = c->d_work_counter;
     cfg.d_stats = c->stats ? c->d_stats : nullptr;
-    cfg.variant = pick_kernel(c, max_depth);
+    cfg.variant = variant >= 0 ? variant : pick_kernel(c, max_depth);
     c->kernel_used = cfg.variant;
     cfg.d_cam_prims = c->d_cam_prims;
     cfg.band = BandSignal{nullptr, nullptr, 0, 0, 1, 1, 1};
@@ -353,6 +389,7 @@ void rt_destroy(rt_ctx* ctx) {
         if (ctx->h_band_flags) cudaFreeHost(ctx->h_band_flags);
         if (ctx->render_stream) cudaStreamDestroy(ctx->render_stream);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+        if (ctx->tune_ev0) { cudaEventDestroy(ctx->tune_ev0); cudaEventDestroy(ctx->tune_ev1); }
     }
     delete ctx;
 }
@@ -370,7 +407,7 @@ int rt_set_spheres(rt_ctx* ctx, const float* cr, const float* mat8, const int32_
     ctx->mat_id.clear();
     ctx->object_id.resize(n);
     for (int64_t i = 0; i < n; ++i) ctx->object_id[i] = object_id ? object_id[i] : (int32_t)i;
-    ctx->bvh_valid = false; ctx->device_valid = false;
+    ctx->bvh_valid = false; ctx->device_valid = false; ctx->tune_state = 0; ctx->tune_pending = -1;
     return 0;
 }
 
@@ -390,7 +427,7 @@ int rt_set_triangles(rt_ctx* ctx, const float* v, const int32_t* material_id, in
         ctx->mat_id[i] = id;
         ctx->object_id[i] = (int32_t)i;
     }
-    ctx->bvh_valid = false; ctx->device_valid = false;
+    ctx->bvh_valid = false; ctx->device_valid = false; ctx->tune_state = 0; ctx->tune_pending = -1;
     return 0;
 }
 
@@ -493,7 +530,7 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
     ctx->aspect = (double)width / height;            // RayTracer::render, old/raytracer_core copy.cpp:259
     CameraBlock cam = camera_block(ctx, ctx->aspect);
     TileMap tm = full_frame_map(width, height);
-    if (pick_kernel(ctx, 1) == 2) {
+    if (is_wavefront(pick_kernel(ctx, 1))) {
         if (int rc = ensure_wave(ctx, task_count(tm), 1, 1)) return rc;
         int nl = 0;
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, true, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t,
@@ -566,7 +603,7 @@ static int render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile
     tm.first_tile = first_tile; tm.tile_stride = tile_stride;
     tm.n_local_tiles = first_tile < tm.n_tiles ? (tm.n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
     tm.compact = layout == 0 ? 1 : 0; tm.skew = layout == 0 ? 0 : 1;
-    if (pick_kernel(ctx, max_depth) == 2 && tm.n_local_tiles) {
+    if (is_wavefront(pick_kernel(ctx, max_depth)) && tm.n_local_tiles) {
         if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
         int nl = 0;
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
@@ -653,18 +690,23 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
     ctx->aspect = (double)width / height;
     CameraBlock cam = camera_block(ctx, ctx->aspect);
     TileMap tm = full_frame_map(width, height);
-    if (pick_kernel(ctx, max_depth) == 2) {
+    const bool tuned = tunes(ctx, max_depth);
+    if (tuned) { if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc; }   // allocate outside the timed events
+    const int variant = tuned ? tune_begin(ctx, (cudaStream_t)stream, (double)width * height * spp) : pick_kernel(ctx, max_depth);
+    if (is_wavefront(variant)) {
         if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
         int nl = 0;
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
-                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream, max_depth), ctx->wave, &nl));
+                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream, max_depth, variant), ctx->wave, &nl));
         ctx->launches += nl;
+        if (tuned) tune_end(ctx, (cudaStream_t)stream);
         return 0;
     }
-    LaunchCfg cfg = launch_cfg(ctx, stream, max_depth);
+    LaunchCfg cfg = launch_cfg(ctx, stream, max_depth, variant);
     if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
+    if (tuned) tune_end(ctx, (cudaStream_t)stream);
     ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
     return 0;
 }
@@ -835,7 +877,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     std::string k(name);
     if (k == "integrator") { if (value != 0 && value != 1) return fail(ctx, "integrator must be 0 (v1) or 1 (v2)"); ctx->integrator = (int)value; }
     else if (k == "stats") ctx->stats = value != 0;
-    else if (k == "kernel") { if (value < -1 || value > 3) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront) or 3 (camera-ray packets)"); ctx->kernel = (int)value; }
+    else if (k == "kernel") { if (value < -1 || value > 4) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront), 3 (camera-ray packets) or 4 (wavefront with packet bounce 0)"); ctx->kernel = (int)value; }
     else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
     else if (k == "overlap") ctx->overlap = value != 0;
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }

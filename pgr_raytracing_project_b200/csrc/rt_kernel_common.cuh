@@ -45,6 +45,36 @@ __device__ __forceinline__ void flush_stats(unsigned long long* d_stats, unsigne
 }
 
 
+// ---- chunked work distribution of the packet kernels (k_packet, k_wf_packet0): see k_packet.
+constexpr int kPacketThreads = 256;
+constexpr int kChunk = 8;
+constexpr unsigned kNoChunk = 0xFFFFFFu;
+
+static __device__ __forceinline__ unsigned take_chunk(unsigned int* global_counter, int n_chunks, const int* __restrict__ order) {
+    const unsigned c = atomicAdd(global_counter, 1u);
+    if (c >= (unsigned)n_chunks) return kNoChunk << 8;
+    return (unsigned)(order ? order[c] : (int)c) << 8;
+}
+
+static __device__ __forceinline__ int chunk_next_block(unsigned* word, unsigned int* global_counter, int n_chunks,
+                                                const int* __restrict__ order, int lane) {
+    unsigned v = 0xFFFFFFFFu;
+    if (lane == 0) {
+        for (;;) {
+            const unsigned old = atomicAdd(word, 1u);
+            const unsigned chunk = old >> 8, off = old & 0xFFu;
+            if (chunk == kNoChunk) break;
+            if (off < (unsigned)kChunk) { v = chunk * kChunk + off; break; }
+            if (off == (unsigned)kChunk) {                       // this warp installs the next chunk
+                atomicExch(word, take_chunk(global_counter, n_chunks, order));
+                continue;
+            }
+            while ((*(volatile unsigned*)word >> 8) == chunk) __nanosleep(32);
+        }
+    }
+    return (int)__shfl_sync(0xffffffffu, v, 0);
+}
+
 template <typename K>
 inline int resident_grid(K kernel, int sm_count) {
     int per_sm = 0;

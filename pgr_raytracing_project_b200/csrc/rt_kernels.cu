@@ -235,35 +235,6 @@ k_cam_tris(const float4* __restrict__ prims, float4* __restrict__ cam_prims, int
 // last offset + 1 fetches the CTA's next chunk from the global counter (one ATOMG per chunk) while
 // the others that run out wait for the word to change.  No CTA barrier, no fixed assignment: load
 // stays balanced to within one block per warp.
-constexpr int kPacketThreads = 256;
-constexpr int kChunk = 8;
-constexpr unsigned kNoChunk = 0xFFFFFFu;
-
-__device__ __forceinline__ unsigned take_chunk(unsigned int* global_counter, int n_chunks, const int* __restrict__ order) {
-    const unsigned c = atomicAdd(global_counter, 1u);
-    if (c >= (unsigned)n_chunks) return kNoChunk << 8;
-    return (unsigned)(order ? order[c] : (int)c) << 8;
-}
-
-__device__ __forceinline__ int chunk_next_block(unsigned* word, unsigned int* global_counter, int n_chunks,
-                                                const int* __restrict__ order, int lane) {
-    unsigned v = 0xFFFFFFFFu;
-    if (lane == 0) {
-        for (;;) {
-            const unsigned old = atomicAdd(word, 1u);
-            const unsigned chunk = old >> 8, off = old & 0xFFu;
-            if (chunk == kNoChunk) break;
-            if (off < (unsigned)kChunk) { v = chunk * kChunk + off; break; }
-            if (off == (unsigned)kChunk) {                       // this warp installs the next chunk
-                atomicExch(word, take_chunk(global_counter, n_chunks, order));
-                continue;
-            }
-            while ((*(volatile unsigned*)word >> 8) == chunk) __nanosleep(32);
-        }
-    }
-    return (int)__shfl_sync(0xffffffffu, v, 0);
-}
-
 // One CTA builds this frame's chunk order from last frame's costs (ChunkSchedule): latest-start-time
 // first.  A chunk's 8 blocks run side by side on the CTA's 8 warps, so its duration is its largest block
 // cost; the frame's length is T = (sum of all block costs) / resident warps; a chunk is due at T, or --
@@ -466,11 +437,7 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
                           uint32_t sample_offset, int resolve, float* d_out, int32_t* d_prim, float* d_t,
                           const LaunchCfg& cfg) {
     int n_work = work_items(tm);
-    if (TRI && sc.n_prims > 0) {
-        int64_t g = ((int64_t)sc.n_prims + 255) / 256;
-        int cap = cfg.sm_count * 8;
-        k_cam_tris<<<(int)(g > cap ? cap : g), 256, 0, cfg.stream>>>(sc.prims, cfg.d_cam_prims, sc.n_prims, cam.px, cam.py, cam.pz);
-    }
+    if (TRI) launch_cam_tris(sc, cam, cfg);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_packet<TRI, STATS, AOV>, kPacketThreads, 0);
     int grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);
@@ -487,6 +454,14 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
 }
 
 }  // namespace
+
+cudaError_t launch_cam_tris(const SceneView& sc, const CameraBlock& cam, const LaunchCfg& cfg) {
+    if (sc.n_prims <= 0) return cudaSuccess;
+    int64_t g = ((int64_t)sc.n_prims + 255) / 256;
+    int cap = cfg.sm_count * 8;
+    k_cam_tris<<<(int)(g > cap ? cap : g), 256, 0, cfg.stream>>>(sc.prims, cfg.d_cam_prims, sc.n_prims, cam.px, cam.py, cam.pz);
+    return cudaGetLastError();
+}
 
 int packet_chunks(const TileMap& tm) { return (work_items(tm) + kChunk - 1) / kChunk; }
 

@@ -66,7 +66,8 @@ struct LaunchCfg {
     unsigned int* d_work_counter;            // zeroed by the launcher on `stream`
     unsigned long long* d_stats;             // [rays, segments, node_records, prim_tests] or nullptr
     int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel, 2 = wavefront,
-                                             // 3 = k_packet (camera rays: warp = packet with one shared stack)
+                                             // 3 = k_packet (camera rays: warp = packet with one shared stack),
+                                             // 4 = wavefront with bounce 0 by packets (k_wf_packet0)
     float4* d_cam_prims;                     // per-frame camera-relative triangle records (3 x float4 per slot)
     BandSignal band;                         // cnt == nullptr: no signalling
     ChunkSchedule sched;                     // order == nullptr: raster order, no cost recording
@@ -90,6 +91,7 @@ cudaError_t launch_wavefront(const SceneView& sc, bool is_tri, bool aov, const C
                              int spp, int max_depth, int integrator, uint64_t seed, uint32_t sample_offset, int resolve,
                              float* d_out, int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb,
                              int* n_launches);
+cudaError_t launch_cam_tris(const SceneView& sc, const CameraBlock& cam, const LaunchCfg& cfg);   // per-frame camera-relative triangle table
 int packet_chunks(const TileMap& tm);      // chunks k_packet cuts this tile map into (ChunkSchedule sizes)
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
                                  int32_t* d_prim, float* d_t, const LaunchCfg& cfg);

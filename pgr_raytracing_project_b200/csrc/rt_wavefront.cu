@@ -78,6 +78,54 @@ k_wf_generate(const __grid_constant__ CameraBlock cam, const __grid_constant__ W
     if (STATS) { Counters c = {0, 0, 0}; flush_stats(d_stats, rays, c); }
 }
 
+// Bounce 0 of a wave for the hybrid variant 4: camera rays are coherent, so generation and the first
+// trace are ONE kernel that walks each 8x4 pixel block as a packet (packet_intersect, the k_packet
+// machinery incl. the CTA-chunked work distribution) -- once per sample of the wave's batch -- and writes
+// ray + closest hit of every path to queue 0, ready for k_wf_shade.  Bounces >= 1 are incoherent and
+// stay with the per-lane k_wf_trace.  Same bits as k_wf_generate + k_wf_trace(0).
+template <bool TRI, bool STATS>
+__global__ void __launch_bounds__(kPacketThreads)
+k_wf_packet0(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_prims, const __grid_constant__ CameraBlock cam,
+             const __grid_constant__ WaveArgs wa, const __grid_constant__ WaveBuffers wb, unsigned int* chunk_counter,
+             unsigned long long* d_stats) {
+    __shared__ uint2 s_stack[kPacketThreads / 32][kStackDepth];
+    __shared__ unsigned s_word;
+    const int lane = threadIdx.x & 31;
+    uint2* stack = s_stack[threadIdx.x >> 5];
+    const int n_blocks = wa.n_tasks_wave >> 5, block0 = wa.task0 >> 5;
+    const int n_chunks = (n_blocks + kChunk - 1) / kChunk;
+    if (threadIdx.x == 0) s_word = take_chunk(chunk_counter, n_chunks, nullptr);
+    __syncthreads();
+    const double inv_w = __ddiv_rn(1.0, (double)wa.tm.width), inv_h = __ddiv_rn(1.0, (double)wa.tm.height);
+    Counters cnt = {0, 0, 0};
+    unsigned long long rays = 0;
+    for (;;) {
+        const int wl = chunk_next_block(&s_word, chunk_counter, n_chunks, nullptr, lane);
+        if (wl < 0) break;
+        if (wl >= n_blocks) continue;
+        PixelWork p = decode_work(wa.tm, block0 + wl, lane);
+        const uint32_t pixel = (uint32_t)(p.j * wa.tm.width + p.i);
+        for (int sb = 0; sb < wa.batch; ++sb) {
+            uint4 ctl = philox4x32_10(pixel, wa.sample_offset + (uint32_t)(wa.sample0 + sb), 0u, 0u, wa.k0, wa.k1);
+            Ray r = camera_ray(cam, p.i, p.j, u01(ctl.x), u01(ctl.y), inv_w, inv_h);
+            Hit h;
+            int work = 0;
+            packet_intersect<TRI, STATS>(sc, cam_prims, r, p.active, lane, stack, h, cnt, work);
+            if (STATS && p.active) rays += 1;
+            const int slot = (wl * 32 + lane) * wa.batch + sb;
+            const unsigned q = warp_append(wb.counters, p.active, lane);
+            if (p.active) {
+                wb.ray_o[0][q] = make_float4(r.ox, r.oy, r.oz, __int_as_float(slot));
+                wb.ray_d[0][q] = make_float4(r.dx, r.dy, r.dz, 0.0f);
+                wb.hit[q] = make_float4(h.t, __int_as_float(h.prim), __int_as_float(h.slot), 0.0f);
+                wb.path_thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+                wb.path_rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+        }
+    }
+    if (STATS) flush_stats(d_stats, rays, cnt);
+}
+
 template <bool TRI, bool STATS>
 __global__ void __launch_bounds__(kThreads)
 k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuffers wb, int bounce, int max_depth, int refill_below,
@@ -216,6 +264,18 @@ template <bool TRI, bool STATS, bool AOV>
 cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const TileMap& tm, int spp, int max_depth,
                           int integrator, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out,
                           int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb, int* n_launches) {
+    const bool packet0 = !AOV && cfg.variant == 4;             // bounce 0 by camera-ray packets
+    if (packet0 && TRI) {
+        cudaError_t e = launch_cam_tris(sc, cam, cfg);
+        if (e != cudaSuccess) return e;
+        *n_launches += 1;
+    }
+    int packet_grid = 0;
+    if (packet0) {
+        int per_sm = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_packet0<TRI, STATS>, kPacketThreads, 0);
+        packet_grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);
+    }
     const int n_tasks = work_items(tm) * 32;
     const int cap = wb.capacity;
     const int chunk = n_tasks < cap ? n_tasks : (cap & ~31);
@@ -234,14 +294,23 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
             wa.resolve = resolve; wa.last_wave = s0 + batch >= spp;
             cudaError_t e = cudaMemsetAsync(wb.counters, 0, sizeof(unsigned int) * 2 * (max_depth + 2), st);
             if (e != cudaSuccess) return e;
-            k_wf_generate<STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(cam, wa, wb, cfg.d_stats);
+            if (packet0) {
+                e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), st);
+                if (e != cudaSuccess) return e;
+                int need = ((nt >> 5) + kChunk - 1) / kChunk;
+                k_wf_packet0<TRI, STATS><<<packet_grid < need ? packet_grid : need, kPacketThreads, 0, st>>>(
+                    sc, cfg.d_cam_prims, cam, wa, wb, cfg.d_work_counter, cfg.d_stats);
+            } else {
+                k_wf_generate<STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(cam, wa, wb, cfg.d_stats);
+            }
             *n_launches += 1;
             int depth = AOV ? 1 : max_depth;
             for (int b = 0; b < depth; ++b) {
-                k_wf_trace<TRI, STATS><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
+                if (!(packet0 && b == 0))
+                    k_wf_trace<TRI, STATS><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
                 k_wf_shade<TRI, STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(sc, wa, wb, b, d_prim, d_t,
                                                                                                       cfg.d_stats);
-                *n_launches += 2;
+                *n_launches += (packet0 && b == 0) ? 1 : 2;
             }
             if (!AOV) {
                 k_wf_accumulate<<<grid_for(nt, 256, cfg.sm_count, 8), 256, 0, st>>>(wa, wb, d_out);
