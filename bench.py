@@ -274,7 +274,12 @@ def main():
     cam = scene.camera
     ctx.set_camera(cam.position, cam.target, cam.up, cam.fov)
     nodes, prim_index = ctx.get_bvh()
-    renderer = DistributedRenderer(ctx, rank, world, mode="peer_samples")
+    # exchange of the per-rank 1-spp partial frames: up to 4 GPUs the render kernels store straight into their plane of
+    # rank 0's shared buffer (peer_samples: measured 0.459 / 0.485 ms per step at N = 2 / 4 against 0.486 / 0.500 with
+    # an NCCL reduce); at 8 GPUs seven 25-MB streams into one GPU plus the 8-plane sum cost more than NCCL's tree
+    # reduce (0.538 vs 0.515 ms), so N = 8 uses "samples" (reduce(SUM) to rank 0 + resolve)
+    exchange_mode = "peer_samples" if world <= 4 else "samples"
+    renderer = DistributedRenderer(ctx, rank, world, mode=exchange_mode)
     spp_total = SPP_PER_GPU * world
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=ctx.device)       # 512 MiB > 126 MB L2
 
@@ -408,10 +413,11 @@ def main():
             "config": {
                 "workload": WORKLOAD, "width": W, "height": H, "spp_per_gpu": SPP_PER_GPU, "spp_total": spp_total,
                 "max_depth": MAX_DEPTH, "n_triangles": N_TRIS, "bvh_nodes": int(len(nodes)),
-                "partition": "single GPU" if world == 1 else
-                             "sample-range: 1 spp of the full frame per GPU, written by the render kernel straight into this "
-                             "rank's plane of rank 0's shared buffer (CUDA IPC, NVLink peer stores); barrier = one-element NCCL "
-                             "all-reduce; rank 0 sums the planes in rank order and resolves; all inside the timed step",
+                "partition": "single GPU" if world == 1 else (
+                    "sample-range: 1 spp of the full frame per GPU, written by the render kernel straight into this rank's "
+                    "plane of rank 0's shared buffer (CUDA IPC, NVLink peer stores); barrier = one-element NCCL all-reduce; "
+                    "rank 0 sums the planes in rank order and resolves; all inside the timed step" if exchange_mode == "peer_samples"
+                    else "sample-range: 1 spp of the full frame per GPU, NCCL reduce(SUM) to rank 0 + resolve, inside the timed step"),
                 "l2": "scene+BVH = 64 MB < 126 MB L2, so a 512 MiB memset flushes L2 before every timed step "
                       "(outside the CUDA-event pairs)",
                 "host_bvh_build_plus_upload_s": round(build_s, 2),

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200rt.so")
+LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(HERE, "libb200rt.so")   # B200RT_LIB: A/B builds (tools/)
 
 # every symbol include/b200rt.h declares (tests check the exports against the header)
 SYMBOLS = [

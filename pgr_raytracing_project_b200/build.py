@@ -30,7 +30,7 @@ def nvcc_path() -> str:
 def flags() -> list:
     return [
         "-gencode", "arch=compute_100a,code=sm_100a",
-        "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
+        "-O3", "-std=c++17", "-lineinfo", "-fmad=false", *os.environ.get("B200RT_NVCC_EXTRA", "").split(),
         "-Xcompiler", "-fPIC,-fopenmp,-O2,-fno-fast-math,-ffp-contract=off",
         "-Xptxas", "-v",
         "-shared",

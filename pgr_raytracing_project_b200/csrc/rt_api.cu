@@ -44,7 +44,10 @@ struct rt_ctx {
     // device copies
     float4* d_nodes = nullptr;
     float4* d_prims = nullptr;
-    float4* d_cam_prims = nullptr;           // triangles: per-frame camera-relative records (k_cam_tris)
+    float4* d_cam_prims = nullptr;           // triangles: camera-relative records (k_cam_tris), valid for cam_table_pos
+    float cam_table_pos[3] = {0, 0, 0};
+    cudaStream_t cam_table_stream = nullptr; // the stream the table was built on (another stream rebuilds: no cross-stream order)
+    bool cam_table_ok = false;               // reset by every scene upload; checked against the camera position per launch
     int* d_slot_prim = nullptr;
     float4* d_mats = nullptr;
     bool device_valid = false;
@@ -116,7 +119,7 @@ int cuda_fail(rt_ctx* c, const char* what, cudaError_t e) {
 void free_device_scene(rt_ctx* c) {
     cudaFree(c->d_nodes); cudaFree(c->d_prims); cudaFree(c->d_cam_prims); cudaFree(c->d_slot_prim); cudaFree(c->d_mats);
     c->d_nodes = c->d_prims = c->d_cam_prims = c->d_mats = nullptr; c->d_slot_prim = nullptr;
-    c->device_valid = false;
+    c->device_valid = false; c->cam_table_ok = false;
 }
 
 // Camera basis exactly as Camera::get_ray builds it (old/raytracer_core copy.h:160-184): forward
@@ -289,6 +292,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
     cfg.variant = variant >= 0 ? variant : pick_kernel(c, max_depth);
     c->kernel_used = cfg.variant;
     cfg.d_cam_prims = c->d_cam_prims;
+    cfg.cam_table_valid = 0;
     cfg.band = BandSignal{nullptr, nullptr, 0, 0, 1, 1, 1};
     cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr};
     cfg.d_block_times = c->stats ? c->d_block_times : nullptr;
@@ -323,8 +327,18 @@ int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm) {
     return 0;
 }
 
+// The camera-relative triangle table depends on the scene and on the camera POSITION only: a launch whose camera
+// sits where the table was built for (progressive batches, a turning camera) reuses it.
+void claim_cam_table(rt_ctx* ctx, LaunchCfg& cfg, const CameraBlock& cam) {
+    if (!ctx->is_tri || (cfg.variant != 3 && cfg.variant != 4)) return;
+    const bool same = ctx->cam_table_ok && ctx->cam_table_stream == cfg.stream && ctx->cam_table_pos[0] == cam.px && ctx->cam_table_pos[1] == cam.py && ctx->cam_table_pos[2] == cam.pz;
+    cfg.cam_table_valid = same ? 1 : 0;
+    ctx->cam_table_pos[0] = cam.px; ctx->cam_table_pos[1] = cam.py; ctx->cam_table_pos[2] = cam.pz;
+    ctx->cam_table_ok = true; ctx->cam_table_stream = cfg.stream;
+}
+
 // launches of one packet-kernel call: k_chunk_order (if scheduled) + k_cam_tris (triangles) + k_packet
-int packet_launches(const rt_ctx* ctx, const LaunchCfg& cfg) { return 1 + (ctx->is_tri ? 1 : 0) + (cfg.sched.order ? 1 : 0); }
+int packet_launches(const rt_ctx* ctx, const LaunchCfg& cfg) { return 1 + ((ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0) + (cfg.sched.order ? 1 : 0); }
 
 TileMap full_frame_map(int width, int height) {
     TileMap tm;
@@ -540,6 +554,7 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
     }
     LaunchCfg cfg = launch_cfg(ctx, stream);
     if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    claim_cam_table(ctx, cfg, cam);
     CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, tm, d_prim, d_t, cfg));
     ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
     return 0;
@@ -606,13 +621,16 @@ static int render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile
     if (is_wavefront(pick_kernel(ctx, max_depth)) && tm.n_local_tiles) {
         if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
         int nl = 0;
+        LaunchCfg wcfg = launch_cfg(ctx, stream, max_depth);
+        claim_cam_table(ctx, wcfg, cam);
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
-                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream, max_depth), ctx->wave, &nl));
+                            resolve, d_out, nullptr, nullptr, wcfg, ctx->wave, &nl));
         ctx->launches += nl;
         return 0;
     }
     LaunchCfg cfg = launch_cfg(ctx, stream, max_depth);
     if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    claim_cam_table(ctx, cfg, cam);
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
     if (tm.n_local_tiles) ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
@@ -696,14 +714,17 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
     if (is_wavefront(variant)) {
         if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
         int nl = 0;
+        LaunchCfg wcfg = launch_cfg(ctx, stream, max_depth, variant);
+        claim_cam_table(ctx, wcfg, cam);
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
-                            resolve, d_out, nullptr, nullptr, launch_cfg(ctx, stream, max_depth, variant), ctx->wave, &nl));
+                            resolve, d_out, nullptr, nullptr, wcfg, ctx->wave, &nl));
         ctx->launches += nl;
         if (tuned) tune_end(ctx, (cudaStream_t)stream);
         return 0;
     }
     LaunchCfg cfg = launch_cfg(ctx, stream, max_depth, variant);
     if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    claim_cam_table(ctx, cfg, cam);
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
     if (tuned) tune_end(ctx, (cudaStream_t)stream);
@@ -787,6 +808,7 @@ static int render_host_overlapped(rt_ctx* ctx, int width, int height, int spp, u
     bs.n_groups = (bs.tiles_x + bs.group_cols - 1) / bs.group_cols;
     const int n_regions = ((bs.tiles_y + bs.band_rows - 1) / bs.band_rows) * bs.n_groups;   // <= 48
     if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    claim_cam_table(ctx, cfg, cam);
     volatile unsigned int* flags = ctx->h_band_flags;
     for (int b = 0; b < n_regions; ++b) flags[b] = 0u;
     CK(cudaMemsetAsync(ctx->d_band_cnt, 0, kMaxBands * sizeof(unsigned int), ctx->render_stream));

@@ -387,8 +387,8 @@ __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* _
             float tl, tr;
             const bool hl = box_hit_oct<OCT>(l0, l1, r, kTMin, h.t, tl);
             const bool hr = box_hit_oct<OCT>(r0, r1, r, kTMin, h.t, tr);
-            const unsigned bl = __ballot_sync(0xffffffffu, hl), br = __ballot_sync(0xffffffffu, hr);
             const int lc = __float_as_int(l0.w), rc = __float_as_int(r0.w);
+            const unsigned bl = __ballot_sync(0xffffffffu, hl), br = __ballot_sync(0xffffffffu, hr);
             if (bl != 0u && br != 0u) {
                 // entry distances with +inf for a missed child: a lane votes "right first" iff tr' < tl'
                 const float tl2 = hl ? tl : __int_as_float(0x7f800000), tr2 = hr ? tr : __int_as_float(0x7f800000);

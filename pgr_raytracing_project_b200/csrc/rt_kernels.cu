@@ -437,7 +437,7 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
                           uint32_t sample_offset, int resolve, float* d_out, int32_t* d_prim, float* d_t,
                           const LaunchCfg& cfg) {
     int n_work = work_items(tm);
-    if (TRI) launch_cam_tris(sc, cam, cfg);
+    if (TRI && !cfg.cam_table_valid) launch_cam_tris(sc, cam, cfg);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_packet<TRI, STATS, AOV>, kPacketThreads, 0);
     int grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);

@@ -68,7 +68,8 @@ struct LaunchCfg {
     int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel, 2 = wavefront,
                                              // 3 = k_packet (camera rays: warp = packet with one shared stack),
                                              // 4 = wavefront with bounce 0 by packets (k_wf_packet0)
-    float4* d_cam_prims;                     // per-frame camera-relative triangle records (3 x float4 per slot)
+    float4* d_cam_prims;                     // camera-relative triangle records (3 x float4 per slot)
+    int cam_table_valid;                     // the table already holds this scene + camera position: skip k_cam_tris
     BandSignal band;                         // cnt == nullptr: no signalling
     ChunkSchedule sched;                     // order == nullptr: raster order, no cost recording
     unsigned long long* d_block_times;       // debug (instrumented k_packet only): [2 * work item] = globaltimer start, end; or nullptr

@@ -265,7 +265,7 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
                           int integrator, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out,
                           int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb, int* n_launches) {
     const bool packet0 = !AOV && cfg.variant == 4;             // bounce 0 by camera-ray packets
-    if (packet0 && TRI) {
+    if (packet0 && TRI && !cfg.cam_table_valid) {
         cudaError_t e = launch_cam_tris(sc, cam, cfg);
         if (e != cudaSuccess) return e;
         *n_launches += 1;
