@@ -88,6 +88,9 @@ struct rt_ctx {
     unsigned int* d_chunk_cost = nullptr;
     int chunk_cap = 0;
     long long chunk_key = -1;
+    int chunk_frames = 0;                    // frames whose costs are in d_chunk_cost since the last rebuild of the order
+    int chunk_age = 0;                       // frames rendered with the current order
+    CameraBlock chunk_cam;                   // camera the current order was built for
     int schedule = 1;                        // option "schedule"
     unsigned long long* d_block_times = nullptr;   // debug option "block_times" (device pointer supplied by the caller)
     int32_t* d_pick = nullptr;               // rt_select_object scratch: org3 dir3 | prim | t
@@ -294,7 +297,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
     cfg.d_cam_prims = c->d_cam_prims;
     cfg.cam_table_valid = 0;
     cfg.band = BandSignal{nullptr, nullptr, 0, 0, 1, 1, 1};
-    cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr};
+    cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr, 0};
     cfg.d_block_times = c->stats ? c->d_block_times : nullptr;
     cfg.refill_below = c->refill;
     cfg.leaf_vote = c->leaf_vote;
@@ -303,8 +306,8 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
 
 // Attach the chunk-cost history to a packet launch over tile map `tm` (ChunkSchedule).  The history is
 // only meaningful for the tile map it was recorded on; any other map starts from raster order.
-int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm) {
-    cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr};
+int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm, const CameraBlock& cam) {
+    cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr, 0};
     if (!ctx->schedule || cfg.variant != 3) return 0;
     const int n_chunks = packet_chunks(tm);
     if (n_chunks <= 0) return 0;
@@ -316,11 +319,21 @@ int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm) {
         ctx->chunk_cap = n_chunks;
     }
     long long key = ((((long long)tm.width * 65537 + tm.height) * 257 + tm.tile_w) * 257 + tm.tile_h) * 1031 + tm.first_tile;
-    key = key * 1031 + tm.tile_stride + 7919LL * tm.compact + 104729LL * tm.n_local_tiles + 15485863LL * tm.skew;
-    if (key != ctx->chunk_key) {
+    key = key * 1031 + tm.tile_stride + 7919LL * tm.compact + 104729LL * tm.n_local_tiles + 15485863LL * tm.skew + (cfg.band.cnt != nullptr ? 32452843LL : 0LL);
+    // the order is rebuilt (k_chunk_order, ~12 us) for a new tile map, whenever the camera has changed since it was
+    // built, on the 2nd frame (first one with costs) and then every 8th frame; in between the costs accumulate
+    const bool new_map = key != ctx->chunk_key;
+    if (new_map) {
         CK(cudaMemsetAsync(ctx->d_chunk_cost, 0, (size_t)ctx->chunk_cap * 2 * sizeof(unsigned int), cfg.stream));
-        ctx->chunk_key = key;
+        ctx->chunk_key = key; ctx->chunk_frames = 0; ctx->chunk_age = 0;
     }
+    const bool cam_moved = std::memcmp(&ctx->chunk_cam, &cam, sizeof(CameraBlock)) != 0;
+    if (new_map || cam_moved || ctx->chunk_age == 1 || ctx->chunk_age >= 8) {
+        cfg.sched.reorder_frames = ctx->chunk_frames > 0 ? ctx->chunk_frames : 1;     // no costs yet: raster order
+        ctx->chunk_frames = 0; ctx->chunk_age = new_map ? 0 : 1; ctx->chunk_cam = cam;
+        if (new_map) ctx->chunk_age = 0;
+    }
+    ctx->chunk_frames += 1; ctx->chunk_age += 1;
     cfg.sched.order = ctx->d_chunk_order;
     cfg.sched.cost_sum = ctx->d_chunk_cost;
     cfg.sched.cost_max = ctx->d_chunk_cost + ctx->chunk_cap;
@@ -338,7 +351,9 @@ void claim_cam_table(rt_ctx* ctx, LaunchCfg& cfg, const CameraBlock& cam) {
 }
 
 // launches of one packet-kernel call: k_chunk_order (if scheduled) + k_cam_tris (triangles) + k_packet
-int packet_launches(const rt_ctx* ctx, const LaunchCfg& cfg) { return 1 + ((ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0) + (cfg.sched.order ? 1 : 0); }
+int packet_launches(const rt_ctx* ctx, const LaunchCfg& cfg) {
+    return 1 + ((ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0) + ((cfg.sched.order && cfg.sched.reorder_frames > 0) ? 1 : 0);
+}
 
 TileMap full_frame_map(int width, int height) {
     TileMap tm;
@@ -553,7 +568,7 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
         return 0;
     }
     LaunchCfg cfg = launch_cfg(ctx, stream);
-    if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    if (int rc = attach_schedule(ctx, cfg, tm, cam)) return rc;
     claim_cam_table(ctx, cfg, cam);
     CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, tm, d_prim, d_t, cfg));
     ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
@@ -629,7 +644,7 @@ static int render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile
         return 0;
     }
     LaunchCfg cfg = launch_cfg(ctx, stream, max_depth);
-    if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    if (int rc = attach_schedule(ctx, cfg, tm, cam)) return rc;
     claim_cam_table(ctx, cfg, cam);
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
@@ -723,7 +738,7 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
         return 0;
     }
     LaunchCfg cfg = launch_cfg(ctx, stream, max_depth, variant);
-    if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    if (int rc = attach_schedule(ctx, cfg, tm, cam)) return rc;
     claim_cam_table(ctx, cfg, cam);
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
@@ -807,7 +822,7 @@ static int render_host_overlapped(rt_ctx* ctx, int width, int height, int spp, u
     bs.group_cols = (bs.tiles_x + want_cols - 1) / want_cols;
     bs.n_groups = (bs.tiles_x + bs.group_cols - 1) / bs.group_cols;
     const int n_regions = ((bs.tiles_y + bs.band_rows - 1) / bs.band_rows) * bs.n_groups;   // <= 48
-    if (int rc = attach_schedule(ctx, cfg, tm)) return rc;
+    if (int rc = attach_schedule(ctx, cfg, tm, cam)) return rc;
     claim_cam_table(ctx, cfg, cam);
     volatile unsigned int* flags = ctx->h_band_flags;
     for (int b = 0; b < n_regions; ++b) flags[b] = 0u;

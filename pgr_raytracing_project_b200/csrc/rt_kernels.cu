@@ -242,9 +242,10 @@ k_cam_tris(const float4* __restrict__ prims, float4* __restrict__ cam_prims, int
 // which its region should be complete (regions in raster order).  key = due - duration, counting-sorted into 256 classes (order
 // inside a class is whatever the atomics give: pure scheduling, pixels do not depend on it).  With one
 // common due date this is longest-processing-time-first.  No history (all zero): raster order.
+// The costs may have been accumulated over n_frames frames (the order is not rebuilt every frame).
 __global__ void __launch_bounds__(1024)
 k_chunk_order(unsigned int* __restrict__ cost_sum, unsigned int* __restrict__ cost_max, int* __restrict__ order, int n,
-              int n_warps, const __grid_constant__ BandSignal band) {
+              int n_warps, int n_frames, const __grid_constant__ BandSignal band) {
     __shared__ unsigned long long s_sum;
     __shared__ unsigned int s_max;
     __shared__ int s_hist[256];
@@ -262,7 +263,7 @@ k_chunk_order(unsigned int* __restrict__ cost_sum, unsigned int* __restrict__ co
         for (int k = tid; k < n; k += 1024) order[k] = k;
         return;
     }
-    const float T = (float)s_sum / (float)(n_warps > 0 ? n_warps : 1);
+    const float T = (float)s_sum / ((float)(n_warps > 0 ? n_warps : 1) * (float)(n_frames > 0 ? n_frames : 1));   // costs of n_frames frames
     const float kmin = -(float)s_max, scale = 255.0f / (T - kmin);
     auto cls_of = [&](int k) {
         float due = T;
@@ -443,9 +444,9 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
     int grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);
     int need = (n_work + kChunk - 1) / kChunk;
     if (grid > need) grid = need;
-    if (cfg.sched.order != nullptr) {
+    if (cfg.sched.order != nullptr && cfg.sched.reorder_frames > 0) {
         k_chunk_order<<<1, 1024, 0, cfg.stream>>>(cfg.sched.cost_sum, cfg.sched.cost_max, cfg.sched.order, need,
-                                                  grid * (kPacketThreads / 32), cfg.band);
+                                                  grid * (kPacketThreads / 32), cfg.sched.reorder_frames, cfg.band);
     }
     k_packet<TRI, STATS, AOV><<<grid, kPacketThreads, 0, cfg.stream>>>(
         sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,

@@ -58,6 +58,7 @@ struct ChunkSchedule {
     int* order;                      // n_chunks entries, written by k_chunk_order, read by k_packet
     unsigned int* cost_sum;          // n_chunks: sum of the chunk's block costs (last frame in, this frame out)
     unsigned int* cost_max;          // n_chunks: largest block cost of the chunk
+    int reorder_frames;              // > 0: rebuild `order` now from the costs of that many frames; 0: keep the order
 };
 
 struct LaunchCfg {
