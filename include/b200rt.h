@@ -182,6 +182,8 @@ int rt_tonemap_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
  * bit-identical results; "refill" 1..32 = share (in 32nds)
  * of a warp's traversing lanes below which it leaves the traversal loop to shade / refill (default
  * 8); "leaf_vote" 1..32 = lanes holding a leaf at which the warp runs the leaf step (default 8);
+ * "builder" 0/1 = what the implicit build of the first render after a scene upload uses (rt_build_bvh's
+ * argument; default 0); "schedule" 0/1 = cost-aware work order of the packet kernel (default 1);
  * "overlap" 0/1 = rt_render_host copies finished bands of a camera-ray frame to the host while the
  * kernel renders the rest (default 1). */
 int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);

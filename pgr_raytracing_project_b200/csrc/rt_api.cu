@@ -16,6 +16,7 @@
 #include "../../include/b200rt.h"
 #include "rt_bvh.h"
 #include "rt_kernels.h"
+#include "rt_lbvh.h"
 
 using namespace b200rt;
 
@@ -40,6 +41,11 @@ struct rt_ctx {
     std::vector<int32_t> prim_index;
     bool bvh_valid = false;
     int bvh_depth = 0;
+    int64_t n_nodes = 0;                 // node records of the current tree (host vector `nodes` may be a stale mirror)
+    float root_extent = 0.0f;            // max |coordinate| of the root box
+    int builder = 0;                     // option "builder": what set_scene -> render builds with (0 host median split, 1 device LBVH)
+    rt_bvh_node* d_nodes_abi = nullptr;  // device-built tree in ABI layout, until the host mirror is asked for (rt_get_bvh)
+    bool host_bvh_stale = false;
 
     // device copies
     float4* d_nodes = nullptr;
@@ -120,7 +126,7 @@ int cuda_fail(rt_ctx* c, const char* what, cudaError_t e) {
     } while (0)
 
 void free_device_scene(rt_ctx* c) {
-    cudaFree(c->d_nodes); cudaFree(c->d_prims); cudaFree(c->d_cam_prims); cudaFree(c->d_slot_prim); cudaFree(c->d_mats);
+    cudaFree(c->d_nodes); cudaFree(c->d_prims); cudaFree(c->d_cam_prims); cudaFree(c->d_nodes_abi); c->d_nodes_abi = nullptr; cudaFree(c->d_slot_prim); cudaFree(c->d_mats);
     c->d_nodes = c->d_prims = c->d_cam_prims = c->d_mats = nullptr; c->d_slot_prim = nullptr;
     c->device_valid = false; c->cam_table_ok = false;
 }
@@ -232,19 +238,15 @@ int ensure_device(rt_ctx* ctx) {
 
 int ensure_bvh(rt_ctx* ctx) {
     if (ctx->bvh_valid) return 0;
-    return rt_build_bvh(ctx, 0);
+    return rt_build_bvh(ctx, ctx->builder);
 }
 
 SceneView scene_view(const rt_ctx* c) {
     SceneView v;
     v.nodes = c->d_nodes; v.prims = c->d_prims; v.slot_prim = c->d_slot_prim; v.mats = c->d_mats;
-    v.n_prims = (int)c->n; v.n_nodes = (int)c->nodes.size();
+    v.n_prims = (int)c->n; v.n_nodes = (int)c->n_nodes;
     v.sane_extent = 0;
-    if (!c->nodes.empty()) {
-        float mx = 0.0f;
-        for (int k = 0; k < 3; ++k) mx = std::fmax(mx, std::fmax(std::fabs(c->nodes[0].bmin[k]), std::fabs(c->nodes[0].bmax[k])));
-        v.sane_extent = mx < 0x1p40f ? 1 : 0;      // NaN compares false
-    }
+    if (c->n_nodes > 0) v.sane_extent = c->root_extent < 0x1p40f ? 1 : 0;      // NaN compares false
     v.bg_r = c->bg[0]; v.bg_g = c->bg[1]; v.bg_b = c->bg[2];
     return v;
 }
@@ -467,10 +469,72 @@ int rt_set_background(rt_ctx* ctx, const float rgb[3]) {
     return 0;
 }
 
+// the host vectors hold the tree: refresh the summary fields
+static void note_host_tree(rt_ctx* ctx) {
+    ctx->n_nodes = (int64_t)ctx->nodes.size();
+    ctx->host_bvh_stale = false;
+    ctx->root_extent = 0.0f;
+    if (!ctx->nodes.empty())
+        for (int k = 0; k < 3; ++k)
+            ctx->root_extent = std::fmax(ctx->root_extent, std::fmax(std::fabs(ctx->nodes[0].bmin[k]), std::fabs(ctx->nodes[0].bmax[k])));
+}
+
+// builder 1: everything on the device (rt_lbvh.cu); the host mirror of the tree (rt_get_bvh, the stack bound) is
+// downloaded afterwards.  Materials are uploaded like ensure_device does.
+static int build_bvh_device(rt_ctx* ctx) {
+    DeviceGuard g(ctx->device);
+    free_device_scene(ctx);
+    ctx->nodes.clear(); ctx->prim_index.clear(); ctx->n_nodes = 0; ctx->root_extent = 0.0f; ctx->host_bvh_stale = false;
+    const int64_t n = ctx->n;
+    if (n > 0) {
+        float* d_raw = nullptr;
+        int* d_mid = nullptr;
+        const size_t raw_bytes = ctx->prim_data.size() * sizeof(float);
+        CK(cudaMalloc(&d_raw, raw_bytes));
+        cudaError_t e = cudaMemcpy(d_raw, ctx->prim_data.data(), raw_bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && ctx->is_tri) {
+            e = cudaMalloc(&d_mid, (size_t)n * sizeof(int));
+            if (e == cudaSuccess) e = cudaMemcpy(d_mid, ctx->mat_id.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice);
+        }
+        LbvhResult r;
+        if (e == cudaSuccess) e = lbvh_build(d_raw, d_mid, ctx->is_tri, (int)n, ctx->sm_count, nullptr, &r);
+        cudaFree(d_raw); cudaFree(d_mid);
+        if (e != cudaSuccess) return cuda_fail(ctx, "rt_build_bvh(device)", e);
+        ctx->d_nodes = r.d_nodes; ctx->d_prims = r.d_prims; ctx->d_slot_prim = r.d_prim_index;
+        ctx->d_nodes_abi = r.d_nodes_abi; ctx->host_bvh_stale = true;
+        ctx->n_nodes = r.n_nodes;
+        rt_bvh_node root;
+        e = cudaMemcpy(&root, r.d_nodes_abi, sizeof(root), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return cuda_fail(ctx, "rt_build_bvh(device): download", e);
+        ctx->root_extent = 0.0f;
+        for (int k = 0; k < 3; ++k) ctx->root_extent = std::fmax(ctx->root_extent, std::fmax(std::fabs(root.bmin[k]), std::fabs(root.bmax[k])));
+        ctx->bvh_depth = r.depth;
+        if (ctx->bvh_depth > kStackDepth - 2) {
+            free_device_scene(ctx);
+            return fail(ctx, "rt_build_bvh: device-built tree deeper than the traversal stack (duplicate primitives?); use builder 0");
+        }
+        if (ctx->is_tri) CK(cudaMalloc(&ctx->d_cam_prims, (size_t)n * 3 * sizeof(float4)));
+    }
+    if (ctx->m > 0) {
+        std::vector<float4> mats((size_t)ctx->m * 2);
+        for (int k = 0; k < ctx->m; ++k) {
+            const float* s = &ctx->mats[8 * (size_t)k];
+            mats[2 * k + 0] = make_float4(s[0], s[1], s[2], s[3]);
+            mats[2 * k + 1] = make_float4(s[4], s[5], s[6], s[7]);
+        }
+        CK(cudaMalloc(&ctx->d_mats, mats.size() * sizeof(float4)));
+        CK(cudaMemcpy(ctx->d_mats, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    }
+    ctx->bvh_valid = true; ctx->device_valid = true;
+    return 0;
+}
+
 int rt_build_bvh(rt_ctx* ctx, int builder) {
     if (!ctx) return 1;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (builder != 0) return fail(ctx, "rt_build_bvh: builder 1 (device LBVH) is not available in this build");
+    if (builder != 0 && builder != 1) return fail(ctx, "rt_build_bvh: builder must be 0 (reference median split, host) or 1 (LBVH, device)");
+    ctx->tune_state = 0; ctx->tune_pending = -1;
+    if (builder == 1) return build_bvh_device(ctx);
     PrimBoxes boxes;
     if (ctx->is_tri) triangle_boxes(ctx->prim_data.data(), ctx->n, boxes);
     else sphere_boxes(ctx->prim_data.data(), ctx->n, boxes);
@@ -479,6 +543,7 @@ int rt_build_bvh(rt_ctx* ctx, int builder) {
     ctx->bvh_depth = validate_bvh(ctx->nodes.data(), (int64_t)ctx->nodes.size(), ctx->n, &msg);
     if (ctx->bvh_depth < 0) return fail(ctx, msg);
     if (ctx->bvh_depth > kStackDepth - 2) return fail(ctx, "rt_build_bvh: tree deeper than the traversal stack");
+    note_host_tree(ctx);
     ctx->bvh_valid = true; ctx->device_valid = false;
     return 0;
 }
@@ -501,6 +566,14 @@ int rt_get_bvh(rt_ctx* ctx, rt_bvh_node* nodes, int64_t* n_nodes, int32_t* prim_
     if (!ctx) return 1;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     if (int rc = ensure_bvh(ctx)) return rc;
+    if (ctx->host_bvh_stale) {                              // device-built tree: fetch the host mirror now
+        DeviceGuard g(ctx->device);
+        ctx->nodes.resize(ctx->n_nodes); ctx->prim_index.resize(ctx->n);
+        CK(cudaMemcpy(ctx->nodes.data(), ctx->d_nodes_abi, (size_t)ctx->n_nodes * sizeof(rt_bvh_node), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ctx->prim_index.data(), ctx->d_slot_prim, (size_t)ctx->n * sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFree(ctx->d_nodes_abi); ctx->d_nodes_abi = nullptr;
+        ctx->host_bvh_stale = false;
+    }
     if (n_nodes) *n_nodes = (int64_t)ctx->nodes.size();
     if (nodes && !ctx->nodes.empty()) std::memcpy(nodes, ctx->nodes.data(), ctx->nodes.size() * sizeof(rt_bvh_node));
     if (prim_index && ctx->n) std::memcpy(prim_index, ctx->prim_index.data(), (size_t)ctx->n * sizeof(int32_t));
@@ -525,6 +598,7 @@ int rt_set_bvh(rt_ctx* ctx, const rt_bvh_node* nodes, int64_t n_nodes, const int
     ctx->nodes.assign(nodes, nodes + n_nodes);
     ctx->prim_index.assign(prim_index, prim_index + ctx->n);
     ctx->bvh_depth = depth;
+    note_host_tree(ctx);
     ctx->bvh_valid = true; ctx->device_valid = false;
     return 0;
 }
@@ -917,6 +991,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "kernel") { if (value < -1 || value > 4) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront), 3 (camera-ray packets) or 4 (wavefront with packet bounce 0)"); ctx->kernel = (int)value; }
     else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
     else if (k == "overlap") ctx->overlap = value != 0;
+    else if (k == "builder") { if (value != 0 && value != 1) return fail(ctx, "builder must be 0 (reference median split, host) or 1 (LBVH, device)"); ctx->builder = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
     else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);
     else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
@@ -939,7 +1014,8 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "sm_count") *value = ctx->sm_count;
     else if (k == "bvh_depth") *value = ctx->bvh_depth;
     else if (k == "n_prims") *value = ctx->n;
-    else if (k == "n_nodes") *value = (int64_t)ctx->nodes.size();
+    else if (k == "n_nodes") *value = ctx->n_nodes;
+    else if (k == "builder") *value = ctx->builder;
     else return fail(ctx, "rt_get_option: unknown option '" + k + "'");
     return 0;
 }

@@ -138,6 +138,68 @@ def test_primary_bit_exact_and_traversal_counts(ctx, make, W, H):
     assert np.array_equal(prim, ob) and np.array_equal(t, otb)
 
 
+@pytest.mark.parametrize("make,W,H", [
+    (lambda: scenes.random_triangles(50_000, seed=11), 320, 200),
+    (lambda: scenes.random_spheres(30_000, seed=5), 320, 200),
+    (lambda: scenes.cornell_box(), 128, 128),
+    (lambda: scenes.default_scene(), 160, 120),
+    (lambda: scenes.random_triangles(3, seed=2, extent=0.5, size=1.0, cam_z=4.0), 64, 48),    # root is a leaf
+    (lambda: scenes.random_triangles(5, seed=3, extent=0.5, size=1.0, cam_z=4.0), 64, 48),    # smallest real tree
+])
+def test_device_built_bvh_gives_the_same_pixels(ctx, make, W, H):
+    """rt_build_bvh builder 1 (LBVH built on the GPU, rt_lbvh.cu): a different tree, the same closest hits -- ids,
+    distances and images bit-identical to the reference-order tree's; the tree is structurally valid (the oracle
+    adopts it through rt_get_bvh -> orc_set_bvh and agrees too)."""
+    s = make()
+    cam = _setup(ctx, s, W, H)                              # builder 0
+    prim0, t0 = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
+    img0 = ctx.render(W, H, 2, 3, seed=13).cpu().numpy()
+    n0 = ctx.get_option("n_nodes")
+    ctx.build_bvh(builder=1)
+    prim1, t1 = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
+    img1 = ctx.render(W, H, 2, 3, seed=13).cpu().numpy()
+    assert np.array_equal(prim0, prim1) and np.array_equal(t0, t1) and np.array_equal(img0, img1)
+    nodes, prim_index = ctx.get_bvh()
+    assert sorted(prim_index.tolist()) == list(range(s.n_prims)) and len(nodes) == ctx.get_option("n_nodes")
+    assert len(nodes) <= max(n0, 2) * 3
+    leaves = nodes[nodes["b"] > 0]
+    assert leaves["b"].sum() == s.n_prims and leaves["b"].max() <= 4
+    o = _oracle_for(ctx, s, cam)
+    op, ot, _ = o.trace_primary(W, H, orc.MODE_NEAR_FIRST)
+    assert np.array_equal(prim1, op) and np.array_equal(t1, ot)
+    ctx.build_bvh(builder=0)
+
+
+def test_device_built_bvh_duplicates_and_size(ctx):
+    """Coincident primitives (equal Morton codes; ties broken by position) and a 1M-triangle build."""
+    import time
+    import torch
+    rng = np.random.default_rng(5)
+    base = scenes.random_triangles(300, seed=9, extent=2.0, size=0.5, cam_z=6.0)
+    v = np.concatenate([base.vertices, base.vertices[:100], base.vertices[:100]])      # every triangle of the first 100 three times
+    ctx.set_triangles(v, None, base.materials)
+    ctx.set_camera(base.camera.position, base.camera.target, base.camera.up, base.camera.fov)
+    ctx.build_bvh(builder=0)
+    p0, t0 = [x.cpu().numpy() for x in ctx.trace_primary(200, 150)]
+    ctx.build_bvh(builder=1)
+    p1, t1 = [x.cpu().numpy() for x in ctx.trace_primary(200, 150)]
+    assert np.array_equal(p0, p1) and np.array_equal(t0, t1)
+    big = scenes.random_triangles(1_000_000)
+    ctx.set_scene(big, build_bvh=False)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    ctx.build_bvh(builder=1)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    ctx.set_camera(big.camera.position, big.camera.target, big.camera.up, big.camera.fov)
+    p1, t1 = ctx.trace_primary(640, 360)
+    ctx.build_bvh(builder=0)
+    p0, t0 = ctx.trace_primary(640, 360)
+    assert torch.equal(p0, p1) and torch.equal(t0, t1)
+    print(f"device LBVH build of 1M triangles incl. upload + host mirror: {dt * 1e3:.1f} ms, depth {ctx.get_option('bvh_depth')}")
+    assert dt < 2.0
+
+
 def test_empty_scene(ctx):
     ctx.set_spheres(np.zeros((0, 4), np.float32), np.zeros((0, 8), np.float32))
     ctx.set_background((0.25, 0.5, 1.0))

@@ -49,6 +49,11 @@ def main():
     for combo in itertools.product(*[opts[n] for n in names]) if names else [()]:
         for n, v in zip(names, combo):
             ctx.set_option(n, v)
+            if n == "builder":
+                torch.cuda.synchronize(); tb = time.time()
+                ctx.build_bvh(v)
+                torch.cuda.synchronize()
+                print(f"  build_bvh(builder={v}): {(time.time() - tb) * 1e3:.1f} ms", flush=True)
         for _ in range(2):
             ctx.render(W, H, spp, depth, seed=1, out=out)
         ms = []
