@@ -171,6 +171,13 @@ int rt_accumulate(rt_ctx* ctx, const float* d_batch, float* d_accum, int64_t n_f
 int rt_tonemap_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_floats, float exposure,
                   void* stream);
 
+/* The whole display chain of the host on the device: tone map as above, then (enhance != 0) the contrast
+ * stretch of interaction.py:1441-1449 -- (x - p2) / (p98 - p2) clipped, p2 / p98 = numpy's percentile(2) /
+ * percentile(98) over all n_floats tone-mapped values (exact order statistics, numpy >= 2 float32 rules) --
+ * then * 255 -> uint8.  enhance == 0 is rt_tonemap_u8. */
+int rt_display_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_floats, float exposure, int enhance,
+                  void* stream);
+
 /* ---- options and counters.  Options: "integrator" 0 = v1 semantics (default; the generation
  * that runs: RR `depth<3 || rand<0.8` unweighted, metal chosen with probability metallic),
  * 1 = v2 semantics (raytracer_core.cpp:317-347); "stats" 0/1; "kernel" -1 = auto (default: picks by

@@ -15,7 +15,7 @@ SYMBOLS = [
     "rt_trace_primary", "rt_trace_rays", "rt_select_object", "rt_render", "rt_render_tiles", "rt_untile",
     "rt_render_host", "rt_accumulate", "rt_tonemap_u8", "rt_set_option", "rt_get_option", "rt_get_stats",
     "rt_reset_stats", "rt_build_bvh_host", "rt_render_sum", "rt_resolve", "rt_render_tiles_frame", "rt_frame_alloc",
-    "rt_frame_free", "rt_frame_open", "rt_frame_close", "rt_resolve_planes",
+    "rt_frame_free", "rt_frame_open", "rt_frame_close", "rt_resolve_planes", "rt_display_u8",
 ]
 
 
@@ -78,6 +78,7 @@ def load():
         "rt_render_host": (ci, [vp, ci, ci, ci, ci, u64, u32, vp]),
         "rt_accumulate": (ci, [vp, vp, vp, i64, ci, ci, vp]),
         "rt_tonemap_u8": (ci, [vp, vp, vp, i64, C.c_float, vp]),
+        "rt_display_u8": (ci, [vp, vp, vp, i64, C.c_float, ci, vp]),
         "rt_set_option": (ci, [vp, C.c_char_p, i64]),
         "rt_get_option": (ci, [vp, C.c_char_p, C.POINTER(i64)]),
         "rt_get_stats": (ci, [vp, C.POINTER(RtStats)]),

@@ -283,6 +283,15 @@ class RenderContext:
                                       self._stream()))
         return out
 
+    def display_u8(self, accum: torch.Tensor, exposure: float = 1.5, enhance: bool = True,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """interaction.py _tone_map + _enhance_display + gui.py uint8 pack, on the device."""
+        if out is None:
+            out = torch.empty(accum.shape, dtype=torch.uint8, device=self.device)
+        self._ck(self.L.rt_display_u8(self.h, accum.data_ptr(), out.data_ptr(), accum.numel(), float(exposure), int(enhance),
+                                      self._stream()))
+        return out
+
     # ------------------------------------------------------------------ options / counters
     def set_option(self, name: str, value: int):
         self._ck(self.L.rt_set_option(self.h, name.encode(), int(value)))

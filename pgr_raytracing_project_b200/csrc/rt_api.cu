@@ -16,6 +16,7 @@
 #include "../../include/b200rt.h"
 #include "rt_bvh.h"
 #include "rt_kernels.h"
+#include "rt_display.h"
 #include "rt_lbvh.h"
 
 using namespace b200rt;
@@ -99,6 +100,8 @@ struct rt_ctx {
     CameraBlock chunk_cam;                   // camera the current order was built for
     int schedule = 1;                        // option "schedule"
     unsigned long long* d_block_times = nullptr;   // debug option "block_times" (device pointer supplied by the caller)
+    void* d_display = nullptr;               // rt_display_u8 scratch (tone-mapped copy, sorted copy, sort workspace)
+    size_t display_bytes = 0;
     int32_t* d_pick = nullptr;               // rt_select_object scratch: org3 dir3 | prim | t
 };
 
@@ -415,7 +418,7 @@ void rt_destroy(rt_ctx* ctx) {
         cudaDeviceSynchronize();
         free_device_scene(ctx);
         free_wave(ctx);
-        cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick);
+        cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick); cudaFree(ctx->d_display);
         cudaFree(ctx->d_band_cnt); cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
         if (ctx->h_band_flags) cudaFreeHost(ctx->h_band_flags);
         if (ctx->render_stream) cudaStreamDestroy(ctx->render_stream);
@@ -979,6 +982,24 @@ int rt_tonemap_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n,
     DeviceGuard g(ctx->device);
     CK(launch_tonemap_u8(d_accum, d_rgb8, n, exposure, (cudaStream_t)stream));
     if (n) ctx->launches += 1;
+    return 0;
+}
+
+int rt_display_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n, float exposure, int enhance, void* stream) {
+    if (!ctx) return 1;
+    if (!enhance) return rt_tonemap_u8(ctx, d_accum, d_rgb8, n, exposure, stream);
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n < 0 || n > 0x7fffffff || (n > 0 && (!d_accum || !d_rgb8))) return fail(ctx, "rt_display_u8: bad arguments");
+    DeviceGuard g(ctx->device);
+    const size_t need = display_scratch_bytes(n);
+    if (need > ctx->display_bytes) {
+        cudaFree(ctx->d_display); ctx->d_display = nullptr; ctx->display_bytes = 0;
+        CK(cudaMalloc(&ctx->d_display, need));
+        ctx->display_bytes = need;
+    }
+    int nl = 0;
+    CK(launch_display_u8(d_accum, d_rgb8, n, exposure, ctx->d_display, ctx->display_bytes, (cudaStream_t)stream, &nl));
+    ctx->launches += nl;
     return 0;
 }
 

@@ -382,6 +382,36 @@ def test_accumulate_and_tonemap_match_numpy(ctx):
     assert np.array_equal(u8, (x * 255).astype(np.uint8))
 
 
+def _numpy_display(acc, exposure, enhance):
+    """interaction.py:1435-1449 + gui.py:73, verbatim."""
+    image = acc * exposure
+    image = image / (1.0 + image)
+    image = np.clip(image, 0.0, 1.0)
+    if enhance:
+        min_val = np.percentile(image, 2)
+        max_val = np.percentile(image, 98)
+        if max_val > min_val:
+            image = np.clip((image - min_val) / (max_val - min_val), 0, 1)
+    return (np.clip(image, 0, 1) * 255).astype(np.uint8)
+
+
+def test_display_chain_matches_numpy(ctx):
+    """rt_display_u8 = _tone_map + _enhance_display + uint8 pack, bit-exact against the host's numpy code."""
+    import torch
+    rng = np.random.default_rng(1)
+    s = scenes.default_scene()
+    _setup(ctx, s, 320, 200)
+    frames = [ctx.render(320, 200, 4, 4, seed=3).cpu().numpy(),                       # a real frame
+              (rng.random((90, 70, 3)) ** 3).astype(np.float32) * 4.0,                # heavy tail
+              np.full((16, 16, 3), 0.25, dtype=np.float32),                           # p2 == p98: no stretch
+              np.linspace(0, 2, 5 * 7 * 3, dtype=np.float32).reshape(5, 7, 3)]
+    for f in frames:
+        for enhance in (True, False):
+            got = ctx.display_u8(torch.from_numpy(f).to(ctx.device), np.float32(1.5), enhance).cpu().numpy()
+            want = _numpy_display(f, np.float32(1.5), enhance)
+            assert np.array_equal(got, want), (f.shape, enhance, np.abs(got.astype(int) - want.astype(int)).max())
+
+
 # ------------------------------------------------------------------ reference-facing module
 def test_raytracer_cpp_drop_in(ctx, golden_dir):
     """The call sequence of interaction.py:575-583,1294-1304 against the shim module."""
