@@ -200,6 +200,22 @@ def test_device_built_bvh_duplicates_and_size(ctx):
     assert dt < 2.0
 
 
+def test_scene_container_with_cached_bvh(ctx, tmp_path):
+    """A scene + BVH saved to the binary container and loaded back (rt_set_bvh: no rebuild) renders the same pixels."""
+    from pgr_raytracing_project_b200 import scene_io
+    s = scenes.random_triangles(20_000, seed=6)
+    W, H = 160, 100
+    _setup(ctx, s, W, H)
+    img = ctx.render(W, H, 2, 3, seed=4).cpu().numpy()
+    path = str(tmp_path / "s.b2rt")
+    scene_io.save_scene(path, s, bvh=ctx.get_bvh())
+    s2, bvh = scene_io.load_scene(path)
+    ctx.set_scene(s2, build_bvh=False)
+    ctx.set_bvh(*bvh)
+    ctx.set_camera(s2.camera.position, s2.camera.target, s2.camera.up, s2.camera.fov)
+    assert np.array_equal(ctx.render(W, H, 2, 3, seed=4).cpu().numpy(), img)
+
+
 def test_empty_scene(ctx):
     ctx.set_spheres(np.zeros((0, 4), np.float32), np.zeros((0, 8), np.float32))
     ctx.set_background((0.25, 0.5, 1.0))
