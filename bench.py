@@ -8,10 +8,10 @@ Workload (BASELINE.json metric "Mrays/s and ms/frame at 1920x1080", configs[2]):
 1M-triangle random mesh (numpy default_rng(20260003)), reference median-split BVH (leaf <= 4),
 camera (0,0,30) -> origin, fov 45, 1920x1080, primary rays: one jittered camera sample per pixel,
 max_depth 1, mean -> sqrt -> clamp into the float32 RGB framebuffer.  A step is one frame.
-At N > 1 the frame is sample-range partitioned: every GPU renders its own 1 spp of the full frame
-(weak scaling: N x 2.07 M rays per step) straight into its plane of rank 0's shared buffer (peer stores
-over NVLink from the render kernel), then a barrier, then rank 0 sums the planes in rank order and
-resolves -- all inside the timed step.
+At N > 1 (weak scaling: N x 2.07 M rays per step) the frame gets N samples per pixel and is tile-partitioned:
+every GPU renders all samples of its 32x32 tiles and stores the resolved pixels straight into rank 0's frame
+(peer stores over NVLink from the kernel), then a barrier -- all inside the timed step; the frame is
+bit-identical to the 1-GPU frame.
 
 One JSON line on stdout (rank 0).  `value` is device-timed with the scene resident in HBM; `e2e`
 is the same frame through the C-ABI host-buffer call (rt_set_camera + rt_render_host: camera in,
@@ -274,11 +274,12 @@ def main():
     cam = scene.camera
     ctx.set_camera(cam.position, cam.target, cam.up, cam.fov)
     nodes, prim_index = ctx.get_bvh()
-    # exchange of the per-rank 1-spp partial frames: up to 4 GPUs the render kernels store straight into their plane of
-    # rank 0's shared buffer (peer_samples: measured 0.459 / 0.485 ms per step at N = 2 / 4 against 0.486 / 0.500 with
-    # an NCCL reduce); at 8 GPUs seven 25-MB streams into one GPU plus the 8-plane sum cost more than NCCL's tree
-    # reduce (0.538 vs 0.515 ms), so N = 8 uses "samples" (reduce(SUM) to rank 0 + resolve)
-    exchange_mode = "peer_samples" if world <= 4 else "samples"
+    # N > 1 (weak scaling, N x 2.07 M rays per step): the frame gets N samples per pixel and is tile-partitioned --
+    # every GPU renders all N samples of ITS 32x32 tiles (skew-dealt so that each rank gets a share of every tile row
+    # and column) and its kernels store the resolved pixels straight into rank 0's frame (CUDA IPC + NVLink peer
+    # stores); a one-element NCCL all-reduce is the barrier.  Bit-identical to the 1-GPU frame with N spp.
+    # BENCH_EXCHANGE=samples|peer_samples selects the sample-range partitions instead.
+    exchange_mode = os.environ.get("BENCH_EXCHANGE", "peer")
     renderer = DistributedRenderer(ctx, rank, world, mode=exchange_mode)
     spp_total = SPP_PER_GPU * world
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=ctx.device)       # 512 MiB > 126 MB L2
@@ -413,11 +414,14 @@ def main():
             "config": {
                 "workload": WORKLOAD, "width": W, "height": H, "spp_per_gpu": SPP_PER_GPU, "spp_total": spp_total,
                 "max_depth": MAX_DEPTH, "n_triangles": N_TRIS, "bvh_nodes": int(len(nodes)),
-                "partition": "single GPU" if world == 1 else (
-                    "sample-range: 1 spp of the full frame per GPU, written by the render kernel straight into this rank's "
-                    "plane of rank 0's shared buffer (CUDA IPC, NVLink peer stores); barrier = one-element NCCL all-reduce; "
-                    "rank 0 sums the planes in rank order and resolves; all inside the timed step" if exchange_mode == "peer_samples"
-                    else "sample-range: 1 spp of the full frame per GPU, NCCL reduce(SUM) to rank 0 + resolve, inside the timed step"),
+                "partition": "single GPU" if world == 1 else {
+                    "peer": "tiles: N spp per pixel, every GPU renders all samples of its skew-dealt 32x32 tiles and stores the "
+                            "resolved pixels straight into rank 0's frame (CUDA IPC, NVLink peer stores from the kernel); barrier = "
+                            "one-element NCCL all-reduce; bit-identical to the 1-GPU frame; all inside the timed step",
+                    "peer_samples": "sample-range: 1 spp of the full frame per GPU, written by the render kernel into this rank's plane "
+                                    "of rank 0's shared buffer (CUDA IPC); barrier; rank 0 sums the planes in rank order and resolves",
+                    "samples": "sample-range: 1 spp of the full frame per GPU, NCCL reduce(SUM) to rank 0 + resolve, inside the timed step",
+                }.get(exchange_mode, exchange_mode),
                 "l2": "scene+BVH = 64 MB < 126 MB L2, so a 512 MiB memset flushes L2 before every timed step "
                       "(outside the CUDA-event pairs)",
                 "host_bvh_build_plus_upload_s": round(build_s, 2),

@@ -100,6 +100,8 @@ struct rt_ctx {
     CameraBlock chunk_cam;                   // camera the current order was built for
     int schedule = 1;                        // option "schedule"
     unsigned long long* d_block_times = nullptr;   // debug option "block_times" (device pointer supplied by the caller)
+    float4* d_planes = nullptr;              // item mode of the packet kernel: sample planes (grow-only)
+    size_t planes_cap = 0;                   // in float4
     void* d_display = nullptr;               // rt_display_u8 scratch (tone-mapped copy, sorted copy, sort workspace)
     size_t display_bytes = 0;
     int32_t* d_pick = nullptr;               // rt_select_object scratch: org3 dir3 | prim | t
@@ -300,6 +302,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
     cfg.variant = variant >= 0 ? variant : pick_kernel(c, max_depth);
     c->kernel_used = cfg.variant;
     cfg.d_cam_prims = c->d_cam_prims;
+    cfg.d_planes = nullptr; cfg.plane_batch = 0;
     cfg.cam_table_valid = 0;
     cfg.band = BandSignal{nullptr, nullptr, 0, 0, 1, 1, 1};
     cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr, 0};
@@ -311,10 +314,32 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
 
 // Attach the chunk-cost history to a packet launch over tile map `tm` (ChunkSchedule).  The history is
 // only meaningful for the tile map it was recorded on; any other map starts from raster order.
-int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm, const CameraBlock& cam) {
+// Multi-sample camera-ray frames run the packet kernel in item mode ((block, sample) work items, rt_kernels.cu):
+// give the launch a planes buffer of up to 512 MB, i.e. plane_batch samples per pass.
+int attach_planes(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm, int spp) {
+    if (cfg.variant != 3 || spp <= 1) return 0;
+    const int64_t n_tasks = task_count(tm);
+    if (n_tasks <= 0) return 0;
+    int64_t batch = ((int64_t)512 << 20) / (n_tasks * (int64_t)sizeof(float4));
+    if (batch > spp) batch = spp;
+    if (batch < 1) return 0;                                // frame too large: sample loop inside the block
+    const size_t need = (size_t)(batch * n_tasks);
+    if (need > ctx->planes_cap) {
+        cudaDeviceSynchronize();
+        cudaFree(ctx->d_planes); ctx->d_planes = nullptr; ctx->planes_cap = 0;
+        CK(cudaMalloc(&ctx->d_planes, need * sizeof(float4)));
+        ctx->planes_cap = need;
+    }
+    cfg.d_planes = ctx->d_planes; cfg.plane_batch = (int)batch;
+    return 0;
+}
+
+int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm, const CameraBlock& cam, int spp = 1) {
     cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr, 0};
     if (!ctx->schedule || cfg.variant != 3) return 0;
-    const int n_chunks = packet_chunks(tm);
+    if (cfg.d_planes && cfg.plane_batch < spp) return 0;     // several sample batches per frame: raster order
+    const int items_per_block = cfg.d_planes ? spp : 1;
+    const int n_chunks = packet_chunks(tm, items_per_block);
     if (n_chunks <= 0) return 0;
     if (n_chunks > ctx->chunk_cap) {
         cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
@@ -324,7 +349,7 @@ int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm, const Camera
         ctx->chunk_cap = n_chunks;
     }
     long long key = ((((long long)tm.width * 65537 + tm.height) * 257 + tm.tile_w) * 257 + tm.tile_h) * 1031 + tm.first_tile;
-    key = key * 1031 + tm.tile_stride + 7919LL * tm.compact + 104729LL * tm.n_local_tiles + 15485863LL * tm.skew + (cfg.band.cnt != nullptr ? 32452843LL : 0LL);
+    key = key * 1031 + tm.tile_stride + 7919LL * tm.compact + 104729LL * tm.n_local_tiles + 15485863LL * tm.skew + (cfg.band.cnt != nullptr ? 32452843LL : 0LL) + 49979687LL * items_per_block;
     // the order is rebuilt (k_chunk_order, ~12 us) for a new tile map, whenever the camera has changed since it was
     // built, on the 2nd frame (first one with costs) and then every 8th frame; in between the costs accumulate
     const bool new_map = key != ctx->chunk_key;
@@ -356,7 +381,11 @@ void claim_cam_table(rt_ctx* ctx, LaunchCfg& cfg, const CameraBlock& cam) {
 }
 
 // launches of one packet-kernel call: k_chunk_order (if scheduled) + k_cam_tris (triangles) + k_packet
-int packet_launches(const rt_ctx* ctx, const LaunchCfg& cfg) {
+int packet_launches(const rt_ctx* ctx, const LaunchCfg& cfg, int spp = 1) {
+    if (cfg.d_planes && spp > 1) {
+        const int passes = (spp + cfg.plane_batch - 1) / cfg.plane_batch;
+        return 2 * passes + ((ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0) + ((cfg.sched.order && cfg.sched.reorder_frames > 0) ? 1 : 0);
+    }
     return 1 + ((ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0) + ((cfg.sched.order && cfg.sched.reorder_frames > 0) ? 1 : 0);
 }
 
@@ -418,7 +447,7 @@ void rt_destroy(rt_ctx* ctx) {
         cudaDeviceSynchronize();
         free_device_scene(ctx);
         free_wave(ctx);
-        cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick); cudaFree(ctx->d_display);
+        cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick); cudaFree(ctx->d_display); cudaFree(ctx->d_planes);
         cudaFree(ctx->d_band_cnt); cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
         if (ctx->h_band_flags) cudaFreeHost(ctx->h_band_flags);
         if (ctx->render_stream) cudaStreamDestroy(ctx->render_stream);
@@ -721,11 +750,12 @@ static int render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile
         return 0;
     }
     LaunchCfg cfg = launch_cfg(ctx, stream, max_depth);
-    if (int rc = attach_schedule(ctx, cfg, tm, cam)) return rc;
+    if (int rc = attach_planes(ctx, cfg, tm, spp)) return rc;
+    if (int rc = attach_schedule(ctx, cfg, tm, cam, spp)) return rc;
     claim_cam_table(ctx, cfg, cam);
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
-    if (tm.n_local_tiles) ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
+    if (tm.n_local_tiles) ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg, spp) : 1;
     return 0;
 }
 
@@ -815,12 +845,13 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
         return 0;
     }
     LaunchCfg cfg = launch_cfg(ctx, stream, max_depth, variant);
-    if (int rc = attach_schedule(ctx, cfg, tm, cam)) return rc;
+    if (int rc = attach_planes(ctx, cfg, tm, spp)) return rc;
+    if (int rc = attach_schedule(ctx, cfg, tm, cam, spp)) return rc;
     claim_cam_table(ctx, cfg, cam);
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
     if (tuned) tune_end(ctx, (cudaStream_t)stream);
-    ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
+    ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg, spp) : 1;
     return 0;
 }
 
@@ -956,7 +987,7 @@ int rt_render_host(rt_ctx* ctx, int width, int height, int spp, int max_depth, u
         ctx->fb_floats = need;
     }
     if (int rc = ensure_device(ctx)) return rc;
-    if (ctx->overlap && pick_kernel(ctx, max_depth) == 3 && max_depth == 1 && ctx->n > 0 && need >= ((size_t)1 << 18)) {
+    if (ctx->overlap && pick_kernel(ctx, max_depth) == 3 && max_depth == 1 && spp == 1 && ctx->n > 0 && need >= ((size_t)1 << 18)) {
         CK(cudaStreamSynchronize(nullptr));               // order after earlier work of the legacy stream
         return render_host_overlapped(ctx, width, height, spp, seed, sample_offset, h_out);
     }

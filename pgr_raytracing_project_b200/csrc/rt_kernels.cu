@@ -297,12 +297,21 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
          const __grid_constant__ TileMap tm, int n_work, int spp, uint32_t k0, uint32_t k1, uint32_t sample_offset,
          int resolve, float* __restrict__ d_out, int32_t* __restrict__ d_prim, float* __restrict__ d_t,
          unsigned int* counter, unsigned long long* d_stats, const __grid_constant__ BandSignal band,
-         const __grid_constant__ ChunkSchedule sched, unsigned long long* d_block_times) {
+         const __grid_constant__ ChunkSchedule sched, unsigned long long* d_block_times, float4* __restrict__ planes,
+         int plane_batch, int plane_sample0) {
+    // planes != nullptr: ITEM MODE for multi-sample frames -- the work item is (block, sample) instead of a block
+    // with a sample loop inside: item = block * plane_batch + sb, sample plane_sample0 + sb, radiance written to
+    // planes[sb][block * 32 + lane]; k_plane_accumulate then adds the planes in sample order (same bits as the
+    // loop) and resolves.  Items of one block are neighbours in the item order, so the 8 warps of a CTA trace
+    // the same block's samples side by side (shared L1 lines), and a frame of few blocks and many samples (one
+    // rank's tiles of a multi-GPU frame) still splits into enough items to balance.
     __shared__ uint2 s_stack[kPacketThreads / 32][kStackDepth];
     __shared__ unsigned s_word;
     const int lane = threadIdx.x & 31;
     uint2* stack = s_stack[threadIdx.x >> 5];
-    const int n_chunks = (n_work + kChunk - 1) / kChunk;
+    const bool item_mode = !AOV && planes != nullptr;
+    const int n_items = item_mode ? n_work * plane_batch : n_work;
+    const int n_chunks = (n_items + kChunk - 1) / kChunk;
     if (threadIdx.x == 0) s_word = take_chunk(counter, n_chunks, sched.order);
     __syncthreads();
     const double inv_w = __ddiv_rn(1.0, (double)tm.width), inv_h = __ddiv_rn(1.0, (double)tm.height);
@@ -310,16 +319,19 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
     Counters cnt = {0, 0, 0};
     unsigned long long rays = 0;
     for (;;) {
-        const int w = chunk_next_block(&s_word, counter, n_chunks, sched.order, lane);
-        if (w < 0) break;
-        if (w >= n_work) continue;
+        const int item = chunk_next_block(&s_word, counter, n_chunks, sched.order, lane);
+        if (item < 0) break;
+        if (item >= n_items) continue;
+        const int w = item_mode ? item / plane_batch : item;
+        const int item_sb = item_mode ? item - w * plane_batch : 0;
         PixelWork p = decode_work(tm, w, lane);
         const uint32_t pixel = (uint32_t)(p.j * tm.width + p.i);
         float sr = 0.0f, sg = 0.0f, sb = 0.0f;
         int work = 0;
         unsigned long long t_start = 0;
         if (STATS && d_block_times) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-        for (int s = 0; s < spp; ++s) {
+        const int s_begin = item_mode ? plane_sample0 + item_sb : 0, s_end = item_mode ? s_begin + 1 : spp;
+        for (int s = s_begin; s < s_end; ++s) {
             float jx = 0.5f, jy = 0.5f;
             if (!AOV) {
                 uint4 ctl = philox4x32_10(pixel, sample_offset + (uint32_t)s, 0u, 0u, k0, k1);
@@ -339,24 +351,25 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
                     float4 m1 = __ldg(sc.mats + 2 * (size_t)material_row<TRI>(sc, h) + 1);
                     cr = __fmaf_rn(1.0f, m1.y, cr); cg = __fmaf_rn(1.0f, m1.z, cg); cb = __fmaf_rn(1.0f, m1.w, cb);
                 }
-                sr = __fadd_rn(sr, cr); sg = __fadd_rn(sg, cg); sb = __fadd_rn(sb, cb);
+                if (item_mode) { if (p.active) planes[(size_t)item_sb * ((size_t)n_work * 32) + (size_t)w * 32 + lane] = make_float4(cr, cg, cb, 0.0f); }
+                else { sr = __fadd_rn(sr, cr); sg = __fadd_rn(sg, cg); sb = __fadd_rn(sb, cb); }
             }
         }
-        if (!AOV && p.active) {
+        if (!AOV && !item_mode && p.active) {
             float* o = d_out + 3 * (size_t)p.out_index;
             if (resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
             else { o[0] = sr; o[1] = sg; o[2] = sb; }
         }
         if (sched.order != nullptr && lane == 0) {
-            atomicAdd(sched.cost_sum + w / kChunk, (unsigned)work);
-            atomicMax(sched.cost_max + w / kChunk, (unsigned)work);
+            atomicAdd(sched.cost_sum + item / kChunk, (unsigned)work);
+            atomicMax(sched.cost_max + item / kChunk, (unsigned)work);
         }
         if (STATS && d_block_times && lane == 0) {
             unsigned long long t_end;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
             d_block_times[2 * (size_t)w] = t_start; d_block_times[2 * (size_t)w + 1] = t_end;
         }
-        if (!AOV && band.cnt != nullptr) {                   // see BandSignal
+        if (!AOV && !item_mode && band.cnt != nullptr) {     // see BandSignal
             __threadfence();                                 // release: this block's pixels before the count
             __syncwarp();
             if (lane == 0) {
@@ -366,6 +379,27 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
         }
     }
     if (STATS) flush_stats(d_stats, rays, cnt);
+}
+
+// Item mode of k_packet, second half: per pixel, add the batch's sample planes IN SAMPLE ORDER to the running sum
+// (kept raw in d_out between batches), resolve after the last batch.  d_out may be a peer GPU's frame.
+__global__ void __launch_bounds__(256)
+k_plane_accumulate(const __grid_constant__ TileMap tm, int n_tasks, int batch, int sample0, int spp, int resolve, int last,
+                   const float4* __restrict__ planes, float* __restrict__ d_out) {
+    const float inv_spp = __fdiv_rn(1.0f, (float)spp);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_tasks; k += gridDim.x * blockDim.x) {
+        PixelWork p = decode_work(tm, k >> 5, k & 31);
+        if (!p.active) continue;
+        float* o = d_out + 3 * (size_t)p.out_index;
+        float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+        if (sample0 > 0) { sr = o[0]; sg = o[1]; sb = o[2]; }
+        for (int s = 0; s < batch; ++s) {
+            const float4 c = planes[(size_t)s * n_tasks + k];
+            sr = __fadd_rn(sr, c.x); sg = __fadd_rn(sg, c.y); sb = __fadd_rn(sb, c.z);
+        }
+        if (last && resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
+        else { o[0] = sr; o[1] = sg; o[2] = sb; }
+    }
 }
 
 __global__ void k_untile(int width, int height, int tile_w, int tile_h, int tiles_x, int n_ranks, int tiles_per_rank,
@@ -442,15 +476,36 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_packet<TRI, STATS, AOV>, kPacketThreads, 0);
     int grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);
-    int need = (n_work + kChunk - 1) / kChunk;
+    const bool item_mode = !AOV && spp > 1 && cfg.d_planes != nullptr && cfg.plane_batch >= 1;
+    const int batch_all = item_mode ? (spp < cfg.plane_batch ? spp : cfg.plane_batch) : 1;
+    int need = (n_work * batch_all + kChunk - 1) / kChunk;
     if (grid > need) grid = need;
     if (cfg.sched.order != nullptr && cfg.sched.reorder_frames > 0) {
         k_chunk_order<<<1, 1024, 0, cfg.stream>>>(cfg.sched.cost_sum, cfg.sched.cost_max, cfg.sched.order, need,
                                                   grid * (kPacketThreads / 32), cfg.sched.reorder_frames, cfg.band);
     }
-    k_packet<TRI, STATS, AOV><<<grid, kPacketThreads, 0, cfg.stream>>>(
-        sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
-        d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times);
+    if (!item_mode) {
+        k_packet<TRI, STATS, AOV><<<grid, kPacketThreads, 0, cfg.stream>>>(
+            sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
+            d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, nullptr, 1, 0);
+        return cudaGetLastError();
+    }
+    // multi-sample frame: (block, sample) items, batches of <= plane_batch samples (the schedule is attached by the
+    // caller only when one batch covers all samples)
+    for (int s0 = 0; s0 < spp; s0 += batch_all) {
+        const int batch = spp - s0 < batch_all ? spp - s0 : batch_all;
+        if (s0 > 0) {
+            cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
+            if (e != cudaSuccess) return e;
+        }
+        k_packet<TRI, STATS, AOV><<<grid, kPacketThreads, 0, cfg.stream>>>(
+            sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
+            d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, cfg.d_planes, batch, s0);
+        const int n_tasks = n_work * 32;
+        int ag = (n_tasks + 255) / 256, acap = cfg.sm_count * 8;
+        k_plane_accumulate<<<ag > acap ? acap : ag, 256, 0, cfg.stream>>>(tm, n_tasks, batch, s0, spp, resolve, s0 + batch >= spp ? 1 : 0,
+                                                                           cfg.d_planes, d_out);
+    }
     return cudaGetLastError();
 }
 
@@ -464,7 +519,7 @@ cudaError_t launch_cam_tris(const SceneView& sc, const CameraBlock& cam, const L
     return cudaGetLastError();
 }
 
-int packet_chunks(const TileMap& tm) { return (work_items(tm) + kChunk - 1) / kChunk; }
+int packet_chunks(const TileMap& tm, int items_per_block) { return (work_items(tm) * items_per_block + kChunk - 1) / kChunk; }
 
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
                                  int32_t* d_prim, float* d_t, const LaunchCfg& cfg) {

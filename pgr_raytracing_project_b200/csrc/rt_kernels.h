@@ -73,6 +73,8 @@ struct LaunchCfg {
     int cam_table_valid;                     // the table already holds this scene + camera position: skip k_cam_tris
     BandSignal band;                         // cnt == nullptr: no signalling
     ChunkSchedule sched;                     // order == nullptr: raster order, no cost recording
+    float4* d_planes;                        // item mode of k_packet (multi-sample frames): sample planes, plane_batch x tasks
+    int plane_batch;                         // samples per batch the planes buffer holds for this tile map (0: loop mode)
     unsigned long long* d_block_times;       // debug (instrumented k_packet only): [2 * work item] = globaltimer start, end; or nullptr
     int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes
     int leaf_vote;                           // phase voting: leaf step when >= this many lanes hold a leaf
@@ -94,7 +96,7 @@ cudaError_t launch_wavefront(const SceneView& sc, bool is_tri, bool aov, const C
                              float* d_out, int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb,
                              int* n_launches);
 cudaError_t launch_cam_tris(const SceneView& sc, const CameraBlock& cam, const LaunchCfg& cfg);   // per-frame camera-relative triangle table
-int packet_chunks(const TileMap& tm);      // chunks k_packet cuts this tile map into (ChunkSchedule sizes)
+int packet_chunks(const TileMap& tm, int items_per_block);   // chunks k_packet cuts this tile map into (ChunkSchedule sizes)
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,
                                  int32_t* d_prim, float* d_t, const LaunchCfg& cfg);
 cudaError_t launch_trace_rays(const SceneView& sc, bool is_tri, const float* d_org, const float* d_dir, int64_t n,
