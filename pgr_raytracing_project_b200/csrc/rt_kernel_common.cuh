@@ -27,6 +27,24 @@ __device__ __forceinline__ PixelWork decode_work(const TileMap& tm, int w, int l
     return p;
 }
 
+// One RGB value per lane for an 8x4 pixel block (lane = row * 8 + column).  The three component stores of
+// 12-byte-strided pixels become, per row, three stores of 8 CONSECUTIVE floats (full 32-byte sectors; 9 shuffles):
+// it matters when the frame lives in another GPU's memory (peer stores over NVLink), where partial sectors are
+// expensive.  Whole warp must call; rows with an inactive pixel (frame edge) fall back to per-pixel stores.
+__device__ __forceinline__ void warp_store_rgb(float* o, bool active, float r, float g, float b, int lane) {
+    if (__all_sync(0xffffffffu, active)) {
+        float* row = o - 3 * (lane & 7);
+        const int q = lane & 7, base = lane & ~7;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int f = q + 8 * k, px = f / 3, c = f - 3 * px;
+            const float vr = __shfl_sync(0xffffffffu, r, base + px), vg = __shfl_sync(0xffffffffu, g, base + px),
+                        vb = __shfl_sync(0xffffffffu, b, base + px);
+            row[f] = c == 0 ? vr : (c == 1 ? vg : vb);
+        }
+    } else if (active) { o[0] = r; o[1] = g; o[2] = b; }
+}
+
 __device__ __forceinline__ int next_work(unsigned int* counter, int lane) {
     unsigned int w = 0;
     if (lane == 0) w = atomicAdd(counter, 1u);

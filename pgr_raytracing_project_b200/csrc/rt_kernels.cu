@@ -355,10 +355,9 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
                 else { sr = __fadd_rn(sr, cr); sg = __fadd_rn(sg, cg); sb = __fadd_rn(sb, cb); }
             }
         }
-        if (!AOV && !item_mode && p.active) {
-            float* o = d_out + 3 * (size_t)p.out_index;
-            if (resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
-            else { o[0] = sr; o[1] = sg; o[2] = sb; }
+        if (!AOV && !item_mode) {
+            if (resolve) { sr = resolve1(sr, inv_spp); sg = resolve1(sg, inv_spp); sb = resolve1(sb, inv_spp); }
+            warp_store_rgb(d_out + 3 * (size_t)p.out_index, p.active, sr, sg, sb, lane);
         }
         if (sched.order != nullptr && lane == 0) {
             atomicAdd(sched.cost_sum + item / kChunk, (unsigned)work);
@@ -387,18 +386,19 @@ __global__ void __launch_bounds__(256)
 k_plane_accumulate(const __grid_constant__ TileMap tm, int n_tasks, int batch, int sample0, int spp, int resolve, int last,
                    const float4* __restrict__ planes, float* __restrict__ d_out) {
     const float inv_spp = __fdiv_rn(1.0f, (float)spp);
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_tasks; k += gridDim.x * blockDim.x) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_tasks; k += gridDim.x * blockDim.x) {   // n_tasks % 32 == 0
         PixelWork p = decode_work(tm, k >> 5, k & 31);
-        if (!p.active) continue;
         float* o = d_out + 3 * (size_t)p.out_index;
         float sr = 0.0f, sg = 0.0f, sb = 0.0f;
-        if (sample0 > 0) { sr = o[0]; sg = o[1]; sb = o[2]; }
-        for (int s = 0; s < batch; ++s) {
-            const float4 c = planes[(size_t)s * n_tasks + k];
-            sr = __fadd_rn(sr, c.x); sg = __fadd_rn(sg, c.y); sb = __fadd_rn(sb, c.z);
+        if (p.active) {
+            if (sample0 > 0) { sr = o[0]; sg = o[1]; sb = o[2]; }
+            for (int s = 0; s < batch; ++s) {
+                const float4 c = planes[(size_t)s * n_tasks + k];
+                sr = __fadd_rn(sr, c.x); sg = __fadd_rn(sg, c.y); sb = __fadd_rn(sb, c.z);
+            }
+            if (last && resolve) { sr = resolve1(sr, inv_spp); sg = resolve1(sg, inv_spp); sb = resolve1(sb, inv_spp); }
         }
-        if (last && resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
-        else { o[0] = sr; o[1] = sg; o[2] = sb; }
+        warp_store_rgb(o, p.active, sr, sg, sb, k & 31);
     }
 }
 

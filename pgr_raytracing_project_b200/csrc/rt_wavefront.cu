@@ -238,19 +238,20 @@ k_wf_shade(const __grid_constant__ SceneView sc, const __grid_constant__ WaveArg
 __global__ void __launch_bounds__(256)
 k_wf_accumulate(const __grid_constant__ WaveArgs wa, const __grid_constant__ WaveBuffers wb, float* __restrict__ d_out) {
     const float inv_spp = __fdiv_rn(1.0f, (float)wa.spp);
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < wa.n_tasks_wave; k += gridDim.x * blockDim.x) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < wa.n_tasks_wave; k += gridDim.x * blockDim.x) {   // whole warps
         int task = wa.task0 + k;
         PixelWork p = decode_work(wa.tm, task >> 5, task & 31);
-        if (!p.active) continue;
         float* o = d_out + 3 * (size_t)p.out_index;
         float sr = 0.0f, sg = 0.0f, sb = 0.0f;
-        if (wa.sample0 > 0) { sr = o[0]; sg = o[1]; sb = o[2]; }
-        for (int s = 0; s < wa.batch; ++s) {
-            float4 rad = wb.path_rad[(size_t)k * wa.batch + s];
-            sr = __fadd_rn(sr, rad.x); sg = __fadd_rn(sg, rad.y); sb = __fadd_rn(sb, rad.z);
+        if (p.active) {
+            if (wa.sample0 > 0) { sr = o[0]; sg = o[1]; sb = o[2]; }
+            for (int s = 0; s < wa.batch; ++s) {
+                float4 rad = wb.path_rad[(size_t)k * wa.batch + s];
+                sr = __fadd_rn(sr, rad.x); sg = __fadd_rn(sg, rad.y); sb = __fadd_rn(sb, rad.z);
+            }
+            if (wa.last_wave && wa.resolve) { sr = resolve1(sr, inv_spp); sg = resolve1(sg, inv_spp); sb = resolve1(sb, inv_spp); }
         }
-        if (wa.last_wave && wa.resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
-        else { o[0] = sr; o[1] = sg; o[2] = sb; }
+        warp_store_rgb(o, p.active, sr, sg, sb, task & 31);
     }
 }
 

@@ -25,6 +25,10 @@ def main():
             opts[k] = [int(x) for x in v.split(",")]
     if which == "c3":
         s, W, H, spp, depth = scenes.random_triangles(1_000_000), 1920, 1080, 1, 1
+    elif which == "c3s8":
+        s, W, H, spp, depth = scenes.random_triangles(1_000_000), 1920, 1080, 8, 1
+    elif which == "c3s2":
+        s, W, H, spp, depth = scenes.random_triangles(1_000_000), 1920, 1080, 2, 1
     elif which == "c3d4":
         s, W, H, spp, depth = scenes.random_triangles(1_000_000), 1920, 1080, 2, 4
     elif which == "c4":
