@@ -360,8 +360,9 @@ def main():
     kernel_name = {0: "k_path<TRI> (persistent path kernel: raygen + BVH traversal + shade + resolve, lane-level continuation)",
                    1: "k_render<TRI> (one-pixel-per-thread megakernel: raygen + BVH traversal + shade + resolve)",
                    2: "k_wf_trace<TRI> (wavefront: generate / trace / shade / accumulate; trace dominates)",
-                   3: "k_packet<TRI> (camera-ray packets: raygen + shared-stack BVH traversal + shade + resolve; "
-                      "kernel_ms includes its per-frame k_cam_tris table pass)"}.get(
+                   3: "k_packet<TRI> (camera-ray packets: raygen + shared-stack BVH traversal + shade + resolve; kernel_ms is the "
+                      "whole rt_render_sum call: k_packet plus, every 8th frame, the 12-us k_chunk_order pass; the k_cam_tris "
+                      "table is reused while the camera position is unchanged)"}.get(
                        ctx.get_option("kernel_used"), "?")
     achieved = rays_per_launch * bytes_per_ray / (kernel_ms / 1e3) / 1e9
     # warm-L2 figure for context (no flush between launches)
