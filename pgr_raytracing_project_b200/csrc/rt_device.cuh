@@ -362,9 +362,7 @@ __device__ __forceinline__ bool box_hit_oct(const float4& lo, const float4& hi, 
 // camera route of the triangle test for a packet: all three record loads issued up front, one
 // combined predicate (det == 0 fails `det > 0` after the sign flip), sign flip as a multiplication
 // by +-1 (exact) so that it runs on the FFMA pipe.  Same bits as test_cam_tri().
-__device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ cam_prims, int slot, const Ray& r, Hit& h) {
-    const float4* p = cam_prims + 3 * (size_t)slot;
-    const float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
+__device__ __forceinline__ void test_cam_tri_records(const float4& r0, const float4& r1, const float4& r2, int slot, const Ray& r, Hit& h) {
     float det = dot3(r.dx, r.dy, r.dz, r0.x, r0.y, r0.z);
     float un = dot3(r.dx, r.dy, r.dz, r1.x, r1.y, r1.z);
     float vn = dot3(r.dx, r.dy, r.dz, r2.x, r2.y, r2.z);
@@ -372,6 +370,10 @@ __device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ c
     det = __fmul_rn(det, sg); un = __fmul_rn(un, sg); vn = __fmul_rn(vn, sg);
     if (det > 0.0f && un >= 0.0f && vn >= 0.0f && __fadd_rn(un, vn) <= det)
         consider(h, __fdiv_rn(__fmul_rn(r0.w, sg), det), __float_as_int(r1.w), slot);
+}
+__device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ cam_prims, int slot, const Ray& r, Hit& h) {
+    const float4* p = cam_prims + 3 * (size_t)slot;
+    test_cam_tri_records(__ldg(p), __ldg(p + 1), __ldg(p + 2), slot, r, h);
 }
 
 template <bool TRI, bool STATS, int OCT>

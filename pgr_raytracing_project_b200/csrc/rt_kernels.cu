@@ -291,7 +291,10 @@ k_chunk_order(unsigned int* __restrict__ cost_sum, unsigned int* __restrict__ co
     for (int k = tid; k < n; k += 1024) { cost_sum[k] = 0u; cost_max[k] = 0u; }
 }
 
-template <bool TRI, bool STATS, bool AOV>
+// ptxas settles at 48 registers = 5 CTAs of 256 threads per SM, the measured optimum: forcing 40 / 32 registers (6 / 8
+// CTAs) spills and is 3 % / 18 % slower, and anything that pushes the kernel to 64 registers (4 CTAs) costs 4-5 % --
+// which is why the final pixel store here is the plain one and not warp_store_rgb
+template <bool TRI, bool STATS, bool AOV, bool ITEM>
 __global__ void __launch_bounds__(kPacketThreads)
 k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_prims, const __grid_constant__ CameraBlock cam,
          const __grid_constant__ TileMap tm, int n_work, int spp, uint32_t k0, uint32_t k1, uint32_t sample_offset,
@@ -309,7 +312,7 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
     __shared__ unsigned s_word;
     const int lane = threadIdx.x & 31;
     uint2* stack = s_stack[threadIdx.x >> 5];
-    const bool item_mode = !AOV && planes != nullptr;
+    constexpr bool item_mode = ITEM && !AOV;
     const int n_items = item_mode ? n_work * plane_batch : n_work;
     const int n_chunks = (n_items + kChunk - 1) / kChunk;
     if (threadIdx.x == 0) s_word = take_chunk(counter, n_chunks, sched.order);
@@ -355,9 +358,10 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
                 else { sr = __fadd_rn(sr, cr); sg = __fadd_rn(sg, cg); sb = __fadd_rn(sb, cb); }
             }
         }
-        if (!AOV && !item_mode) {
-            if (resolve) { sr = resolve1(sr, inv_spp); sg = resolve1(sg, inv_spp); sb = resolve1(sb, inv_spp); }
-            warp_store_rgb(d_out + 3 * (size_t)p.out_index, p.active, sr, sg, sb, lane);
+        if (!AOV && !item_mode && p.active) {              // (plain stores: the warp transpose costs this kernel registers)
+            float* o = d_out + 3 * (size_t)p.out_index;
+            if (resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
+            else { o[0] = sr; o[1] = sg; o[2] = sb; }
         }
         if (sched.order != nullptr && lane == 0) {
             atomicAdd(sched.cost_sum + item / kChunk, (unsigned)work);
@@ -474,7 +478,7 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
     int n_work = work_items(tm);
     if (TRI && !cfg.cam_table_valid) launch_cam_tris(sc, cam, cfg);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_packet<TRI, STATS, AOV>, kPacketThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_packet<TRI, STATS, AOV, false>, kPacketThreads, 0);
     int grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);
     const bool item_mode = !AOV && spp > 1 && cfg.d_planes != nullptr && cfg.plane_batch >= 1;
     const int batch_all = item_mode ? (spp < cfg.plane_batch ? spp : cfg.plane_batch) : 1;
@@ -485,7 +489,7 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
                                                   grid * (kPacketThreads / 32), cfg.sched.reorder_frames, cfg.band);
     }
     if (!item_mode) {
-        k_packet<TRI, STATS, AOV><<<grid, kPacketThreads, 0, cfg.stream>>>(
+        k_packet<TRI, STATS, AOV, false><<<grid, kPacketThreads, 0, cfg.stream>>>(
             sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
             d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, nullptr, 1, 0);
         return cudaGetLastError();
@@ -498,7 +502,7 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
             cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
             if (e != cudaSuccess) return e;
         }
-        k_packet<TRI, STATS, AOV><<<grid, kPacketThreads, 0, cfg.stream>>>(
+        k_packet<TRI, STATS, false, true><<<grid, kPacketThreads, 0, cfg.stream>>>(
             sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
             d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, cfg.d_planes, batch, s0);
         const int n_tasks = n_work * 32;

@@ -46,3 +46,13 @@ def test_node_layout_is_32_bytes():
     from pgr_raytracing_project_b200.context import NODE_DTYPE
     assert NODE_DTYPE.itemsize == 32
     assert NODE_DTYPE.fields["a"][1] == 12 and NODE_DTYPE.fields["bmax"][1] == 16 and NODE_DTYPE.fields["b"][1] == 28
+
+
+def test_headline_kernel_register_budget():
+    """Performance guard (no GPU needed): the camera-ray packet kernel is tuned for 5 CTAs of 256 threads per SM, i.e.
+    at most 48 registers per thread; 64 registers (4 CTAs) measured 4-5 % slower on the C3 benchmark."""
+    build.build(force=not os.path.exists(os.path.join(os.path.dirname(_lib.LIB_PATH), "build.log")))
+    log = open(os.path.join(os.path.dirname(_lib.LIB_PATH), "build.log")).read()
+    m = re.search(r"Compiling entry function '[^']*k_packetILb1ELb0ELb0ELb0E[^']*'.*?Used (\d+) registers", log, flags=re.S)
+    assert m, "k_packet<TRI, !STATS, !AOV, !ITEM> not found in the ptxas log"
+    assert int(m.group(1)) <= 48, f"k_packet uses {m.group(1)} registers"
