@@ -38,7 +38,7 @@
  *   pixel loop, mean, sqrt, clamp . cpp_raytracer/raytracer_core.cpp:381-409
  * Deliberate, documented departures (DESIGN.md "Arithmetic contract"): Philox4x32-10
  * counter RNG instead of PCG32/mt19937; closest-hit ties go to the lower primitive index;
- * triangle primitive (Moller-Trumbore in triple-product form, see test_tri) added; node boxes padded by 2^-16 * scene scale.
+ * triangle primitive (Moller-Trumbore, see test_tri_cam / test_tri_mt) added; node boxes padded by 2^-16 * scene scale.
  *
  * Arithmetic contract (shared with the CUDA kernels, written independently there): IEEE
  * float32, no implicit contraction (compile with -ffp-contract=off, no -ffast-math), explicit
@@ -365,46 +365,64 @@ static inline void test_sphere(const scene_t* s, int32_t prim, const ray_t* r, f
     consider(h, t, prim, tmin);
 }
 
-/* Ray/triangle test (an extension: the reference has no triangle primitive).  Moller-Trumbore
- * written as scalar triple products of the ray direction d with three vectors that depend only on
- * the triangle and the ray ORIGIN:   det = d.(e2 x e1),  u*det = d.(e2 x s),  v*det = d.(s x e1),
- * t*det = e2.(s x e1),  s = o - v0.  The inside test is division-free (compare against det after
- * making det positive; negation is exact), the hit distance is one IEEE division.  The CUDA
- * kernels evaluate the same expression tree; for camera rays (one shared origin) they read
- * (e2 x e1, e2 x s, s x e1, e2.(s x e1)) from a per-frame table computed with these very
- * operations, so both routes give the same bits.  The cross products are the exactly antisymmetric
- * cross_as(): for two triangles that share v0 and an edge vector (the two halves of a quad) u*det of
- * one is then exactly -v*det of the other, so a ray through the shared edge is accepted by at least
- * one of them (no cracks along quad diagonals). */
-static inline void test_tri(const scene_t* s, int32_t prim, const ray_t* r, float tmin, hit_t* h) {
+/* Ray/triangle tests (an extension: the reference has no triangle primitive).  Two routes, the same rule as the
+ * CUDA kernels (rt_device.cuh):
+ *
+ * CAMERA RAYS (bounce 0 of every path, orc_trace_primary): Moller-Trumbore written as scalar triple products of
+ * the ray direction d with three vectors that depend only on the triangle and the ray ORIGIN:
+ *   det = d.(e2 x e1),  u*det = d.(e2 x s),  v*det = d.(s x e1),  t*det = e2.(s x e1),  s = o - v0.
+ * The kernels read the three vectors and the scalar from a per-camera table computed with these very operations.
+ * The cross products are the exactly antisymmetric cross_as(): for two triangles that share v0 and an edge
+ * vector (the two halves of a quad) u*det of one is exactly -v*det of the other, so a camera ray through the shared
+ * edge is accepted by at least one of them (no cracks along quad diagonals).
+ *
+ * ANY OTHER RAY (bounces >= 1, orc_trace_rays): classic Moller-Trumbore, p = d x e2, q = s x e1, det = e1.p,
+ * u*det = s.p, v*det = d.q, t*det = e2.q.
+ *
+ * Both: inside test division-free (compare against det after making det positive; multiplying by -1 is exact),
+ * hit distance one IEEE division. */
+static inline void tri_accept(hit_t* h, float det, float un, float vn, float c, int32_t prim, float tmin) {
+    float sg = det < 0.0f ? -1.0f : 1.0f;
+    det = det * sg; un = un * sg; vn = vn * sg;
+    if (det > 0.0f && un >= 0.0f && vn >= 0.0f && un + vn <= det) consider(h, (c * sg) / det, prim, tmin);
+}
+
+static inline void test_tri_cam(const scene_t* s, int32_t prim, const ray_t* r, float tmin, hit_t* h) {
     const float* p = s->v0e + 9 * (int64_t)prim;
     v3 v0 = {p[0], p[1], p[2]}, e1 = {p[3], p[4], p[5]}, e2 = {p[6], p[7], p[8]};
     v3 sv = sub3(r->o, v0);
     v3 nn = cross_as(e2, e1);
-    float det = dot3(r->d, nn);
-    if (det == 0.0f) return;
     v3 av = cross_as(e2, sv);
-    float un = dot3(r->d, av);
     v3 bv = cross_as(sv, e1);
-    float vn = dot3(r->d, bv);
-    float c = dot3(e2, bv);
-    if (det < 0.0f) { det = -det; un = -un; vn = -vn; c = -c; }
-    if (!(un >= 0.0f && vn >= 0.0f && un + vn <= det)) return;
-    consider(h, c / det, prim, tmin);
+    tri_accept(h, dot3(r->d, nn), dot3(r->d, av), dot3(r->d, bv), dot3(e2, bv), prim, tmin);
 }
 
-static inline void test_prim(const scene_t* s, int32_t prim, const ray_t* r, float tmin, hit_t* h) {
+static inline void test_tri_mt(const scene_t* s, int32_t prim, const ray_t* r, float tmin, hit_t* h) {
+    const float* p = s->v0e + 9 * (int64_t)prim;
+    v3 v0 = {p[0], p[1], p[2]}, e1 = {p[3], p[4], p[5]}, e2 = {p[6], p[7], p[8]};
+    v3 pv = cross3(r->d, e2);
+    float det = dot3(e1, pv);
+    v3 sv = sub3(r->o, v0);
+    float un = dot3(sv, pv);
+    v3 qv = cross3(sv, e1);
+    tri_accept(h, det, un, dot3(r->d, qv), dot3(e2, qv), prim, tmin);
+}
+
+static inline void test_prim(const scene_t* s, int32_t prim, const ray_t* r, float tmin, hit_t* h, int cam) {
     h->n_prim++;
-    if (s->is_tri) test_tri(s, prim, r, tmin, h); else test_sphere(s, prim, r, tmin, h);
+    if (!s->is_tri) test_sphere(s, prim, r, tmin, h);
+    else if (cam) test_tri_cam(s, prim, r, tmin, h);
+    else test_tri_mt(s, prim, r, tmin, h);
 }
 
 enum { MODE_BRUTE = 0, MODE_REF_ORDER = 1, MODE_NEAR_FIRST = 2 };
 
-static void intersect(const scene_t* s, const ray_t* r, float tmin, float tmax, int mode, hit_t* h) {
+/* cam: the ray is a camera ray (triangle route, see above) */
+static void intersect(const scene_t* s, const ray_t* r, float tmin, float tmax, int mode, hit_t* h, int cam) {
     h->t = tmax; h->prim = -1;
     if (s->n == 0) return;
     if (mode == MODE_BRUTE || !s->nodes) {           /* Scene::hit brute force, old/..core copy.cpp:117-130 */
-        for (int64_t i = 0; i < s->n; ++i) test_prim(s, (int32_t)i, r, tmin, h);
+        for (int64_t i = 0; i < s->n; ++i) test_prim(s, (int32_t)i, r, tmin, h, cam);
         return;
     }
     if (mode == MODE_REF_ORDER) {
@@ -415,7 +433,7 @@ static void intersect(const scene_t* s, const ray_t* r, float tmin, float tmax, 
             const node_t* nd = &s->nodes[stack[--sp]];
             float tn; h->n_node++;
             if (!box_hit(nd, r, tmin, h->t, &tn)) continue;
-            if (nd->b > 0) { for (int k = 0; k < nd->b; ++k) test_prim(s, s->prim_index[nd->a + k], r, tmin, h); }
+            if (nd->b > 0) { for (int k = 0; k < nd->b; ++k) test_prim(s, s->prim_index[nd->a + k], r, tmin, h, cam); }
             else { stack[sp++] = nd->a; stack[sp++] = nd->a + 1; }
         }
         return;
@@ -442,7 +460,7 @@ static void intersect(const scene_t* s, const ray_t* r, float tmin, float tmax, 
                 } else if (hl) { ca = L->a; cb = L->b; continue; }
                 else if (hr) { ca = R->a; cb = R->b; continue; }
             } else {
-                for (int k = 0; k < cb; ++k) test_prim(s, s->prim_index[ca + k], r, tmin, h);
+                for (int k = 0; k < cb; ++k) test_prim(s, s->prim_index[ca + k], r, tmin, h, cam);
             }
             int found = 0;
             while (sp > 0) { --sp; if (stack[sp].tn <= h->t) { ca = stack[sp].a; cb = stack[sp].b; found = 1; break; } }
@@ -484,7 +502,7 @@ void orc_trace_primary(const scene_t* s, int W, int H, int mode, int32_t* prim, 
         for (int i = 0; i < W; ++i) {
             ray_t r = camera_ray(s, i, j, 0.5f, 0.5f, inv_w, inv_h);
             hit_t h; h.n_node = 0; h.n_prim = 0;
-            intersect(s, &r, T_MIN, T_MAX, mode, &h);
+            intersect(s, &r, T_MIN, T_MAX, mode, &h, 1);
             int64_t p = (int64_t)j * W + i;
             prim[p] = h.prim; t[p] = h.prim >= 0 ? h.t : 0.0f;
             nn += h.n_node; np += h.n_prim;
@@ -502,7 +520,7 @@ void orc_trace_rays(const scene_t* s, const float* org, const float* dir, int64_
         v3 o = {org[3 * k], org[3 * k + 1], org[3 * k + 2]}, d = {dir[3 * k], dir[3 * k + 1], dir[3 * k + 2]};
         ray_t r = make_ray(o, normalize3(d));
         hit_t h; h.n_node = 0; h.n_prim = 0;
-        intersect(s, &r, T_MIN, T_MAX, mode, &h);
+        intersect(s, &r, T_MIN, T_MAX, mode, &h, 0);
         prim[k] = h.prim; t[k] = h.prim >= 0 ? h.t : 0.0f;
         nn += h.n_node; np += h.n_prim;
     }
@@ -545,7 +563,7 @@ static v3 radiance(const scene_t* s, int i, int j, int W, uint32_t sample, int m
     v3 color = {0, 0, 0}, thr = {1, 1, 1};
     for (int b = 0; b < max_depth; ++b) {
         hit_t h; h.n_node = 0; h.n_prim = 0;
-        intersect(s, &r, T_MIN, T_MAX, mode, &h);
+        intersect(s, &r, T_MIN, T_MAX, mode, &h, b == 0);
         (*segments)++; *n_node += h.n_node; *n_prim += h.n_prim;
         if (h.prim < 0) {                              /* miss: background */
             color.x = fmaf(thr.x, s->bg[0], color.x); color.y = fmaf(thr.y, s->bg[1], color.y); color.z = fmaf(thr.z, s->bg[2], color.z);

@@ -248,7 +248,7 @@ int ensure_bvh(rt_ctx* ctx) {
 
 SceneView scene_view(const rt_ctx* c) {
     SceneView v;
-    v.nodes = c->d_nodes; v.prims = c->d_prims; v.slot_prim = c->d_slot_prim; v.mats = c->d_mats;
+    v.nodes = c->d_nodes; v.prims = c->d_prims; v.cam_prims = c->d_cam_prims; v.slot_prim = c->d_slot_prim; v.mats = c->d_mats;
     v.n_prims = (int)c->n; v.n_nodes = (int)c->n_nodes;
     v.sane_extent = 0;
     if (c->n_nodes > 0) v.sane_extent = c->root_extent < 0x1p40f ? 1 : 0;      // NaN compares false
@@ -373,7 +373,7 @@ int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm, const Camera
 // The camera-relative triangle table depends on the scene and on the camera POSITION only: a launch whose camera
 // sits where the table was built for (progressive batches, a turning camera) reuses it.
 void claim_cam_table(rt_ctx* ctx, LaunchCfg& cfg, const CameraBlock& cam) {
-    if (!ctx->is_tri || (cfg.variant != 3 && cfg.variant != 4)) return;
+    if (!ctx->is_tri) return;
     const bool same = ctx->cam_table_ok && ctx->cam_table_stream == cfg.stream && ctx->cam_table_pos[0] == cam.px && ctx->cam_table_pos[1] == cam.py && ctx->cam_table_pos[2] == cam.pz;
     cfg.cam_table_valid = same ? 1 : 0;
     ctx->cam_table_pos[0] = cam.px; ctx->cam_table_pos[1] = cam.py; ctx->cam_table_pos[2] = cam.pz;
@@ -381,12 +381,13 @@ void claim_cam_table(rt_ctx* ctx, LaunchCfg& cfg, const CameraBlock& cam) {
 }
 
 // launches of one packet-kernel call: k_chunk_order (if scheduled) + k_cam_tris (triangles) + k_packet
-int packet_launches(const rt_ctx* ctx, const LaunchCfg& cfg, int spp = 1) {
-    if (cfg.d_planes && spp > 1) {
-        const int passes = (spp + cfg.plane_batch - 1) / cfg.plane_batch;
-        return 2 * passes + ((ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0) + ((cfg.sched.order && cfg.sched.reorder_frames > 0) ? 1 : 0);
-    }
-    return 1 + ((ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0) + ((cfg.sched.order && cfg.sched.reorder_frames > 0) ? 1 : 0);
+// kernels of one launch_render / launch_trace_primary call (every variant builds the camera table when it is stale)
+int render_launches(const rt_ctx* ctx, const LaunchCfg& cfg, int spp = 1) {
+    const int table = (ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0;
+    if (cfg.variant != 3) return 1 + table;
+    const int order = (cfg.sched.order && cfg.sched.reorder_frames > 0) ? 1 : 0;
+    if (cfg.d_planes && spp > 1) return 2 * ((spp + cfg.plane_batch - 1) / cfg.plane_batch) + table + order;
+    return 1 + table + order;
 }
 
 TileMap full_frame_map(int width, int height) {
@@ -668,8 +669,9 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
     if (is_wavefront(pick_kernel(ctx, 1))) {
         if (int rc = ensure_wave(ctx, task_count(tm), 1, 1)) return rc;
         int nl = 0;
-        CK(launch_wavefront(scene_view(ctx), ctx->is_tri, true, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t,
-                            launch_cfg(ctx, stream), ctx->wave, &nl));
+        LaunchCfg wcfg = launch_cfg(ctx, stream);
+        claim_cam_table(ctx, wcfg, cam);
+        CK(launch_wavefront(scene_view(ctx), ctx->is_tri, true, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t, wcfg, ctx->wave, &nl));
         ctx->launches += nl;
         return 0;
     }
@@ -677,7 +679,7 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
     if (int rc = attach_schedule(ctx, cfg, tm, cam)) return rc;
     claim_cam_table(ctx, cfg, cam);
     CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, tm, d_prim, d_t, cfg));
-    ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg) : 1;
+    ctx->launches += render_launches(ctx, cfg);
     return 0;
 }
 
@@ -755,7 +757,7 @@ static int render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile
     claim_cam_table(ctx, cfg, cam);
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
-    if (tm.n_local_tiles) ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg, spp) : 1;
+    if (tm.n_local_tiles) ctx->launches += render_launches(ctx, cfg, spp);
     return 0;
 }
 
@@ -851,7 +853,7 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset, resolve,
                      d_out, cfg));
     if (tuned) tune_end(ctx, (cudaStream_t)stream);
-    ctx->launches += cfg.variant == 3 ? packet_launches(ctx, cfg, spp) : 1;
+    ctx->launches += render_launches(ctx, cfg, spp);
     return 0;
 }
 
@@ -936,7 +938,7 @@ static int render_host_overlapped(rt_ctx* ctx, int width, int height, int spp, u
     for (int b = 0; b < n_regions; ++b) flags[b] = 0u;
     CK(cudaMemsetAsync(ctx->d_band_cnt, 0, kMaxBands * sizeof(unsigned int), ctx->render_stream));
     CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, 1, ctx->integrator, seed, sample_offset, 1, ctx->d_fb, cfg));
-    ctx->launches += packet_launches(ctx, cfg);
+    ctx->launches += render_launches(ctx, cfg);
     static const bool trace = std::getenv("B200RT_TRACE") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
     auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };

@@ -35,6 +35,7 @@ struct CameraBlock {              // basis in double: primary directions are rou
 struct SceneView {
     const float4* __restrict__ nodes;      // 2 x float4 per 32-byte node: bmin | code, bmax | 0 (see intersect())
     const float4* __restrict__ prims;      // leaf order; triangle: v0|prim, e1|material, e2|0 ; sphere: c|r
+    const float4* __restrict__ cam_prims;  // triangles: camera-relative records for the current camera position (k_cam_tris)
     const int* __restrict__ slot_prim;     // slot -> primitive number (upload order)
     const float4* __restrict__ mats;       // 2 x float4 per material: albedo|metallic, roughness|emission
     int n_prims;
@@ -133,23 +134,26 @@ __device__ __forceinline__ void consider(Hit& h, float t, int prim, int slot) {
     if (t < h.t || h.prim < 0 || prim < h.prim) { h.t = t; h.prim = prim; h.slot = slot; }
 }
 
-// Ray/triangle test: Moller-Trumbore as scalar triple products of the direction d with vectors that
-// depend only on the triangle and the ray origin (s = o - v0):
+// Ray/triangle tests (an extension: the reference has no triangles).  Two routes, the same rule on both sides
+// of the parity check (oracle/rt_oracle.c test_tri_cam / test_tri_mt):
+//
+// CAMERA RAYS (bounce 0 of every path, the primary-hit query; one shared origin): Moller-Trumbore written as scalar
+// triple products of the direction d with vectors that depend only on the triangle and the ORIGIN (s = o - v0):
 //   det = d.(e2 x e1)   u*det = d.(e2 x s)   v*det = d.(s x e1)   t*det = e2.(s x e1)
-// inside test division-free (against det made positive; negation is exact), distance = one IEEE
-// division.  tri_finish() is shared by the general route (vectors computed per ray) and the camera
-// route (vectors read from the per-frame table written by cam_tri_record for the shared origin), so
-// both give the same bits -- and so does oracle/rt_oracle.c test_tri.
-__device__ __forceinline__ void tri_finish(Hit& h, float dx, float dy, float dz, float nx, float ny, float nz,
-                                           float ax, float ay, float az, float bx, float by, float bz, float c,
-                                           int prim, int slot) {
-    float det = dot3(dx, dy, dz, nx, ny, nz);
-    if (det == 0.0f) return;
-    float un = dot3(dx, dy, dz, ax, ay, az);
-    float vn = dot3(dx, dy, dz, bx, by, bz);
-    if (det < 0.0f) { det = -det; un = -un; vn = -vn; c = -c; }
-    if (!(un >= 0.0f && vn >= 0.0f && __fadd_rn(un, vn) <= det)) return;
-    consider(h, __fdiv_rn(c, det), prim, slot);
+// The three vectors and the scalar are a per-camera table (cam_tri_record, written by k_cam_tris), so the test is
+// three dot products; inside test division-free against det made positive (negation is exact), distance = one IEEE
+// division.  The cross products are exactly antisymmetric (cross_as), so the two halves of a quad (shared v0 and
+// edge vector) have u*det of one equal to -v*det of the other: no cracks along quad diagonals in what the camera
+// sees.
+//
+// ANY OTHER RAY (bounces >= 1, rt_trace_rays): classic Moller-Trumbore, p = d x e2, q = s x e1, det = e1.p,
+// u*det = s.p, v*det = d.q, t*det = e2.q, with the same division-free inside test -- 15 fewer operations per
+// test than evaluating the table vectors per ray, and the triangle test is half of the incoherent-bounce kernel.
+__device__ __forceinline__ void tri_accept(Hit& h, float det, float un, float vn, float c, int prim, int slot) {
+    const float sg = det < 0.0f ? -1.0f : 1.0f;              // sign flip as a multiplication by +-1 (exact; FFMA pipe)
+    det = __fmul_rn(det, sg); un = __fmul_rn(un, sg); vn = __fmul_rn(vn, sg);
+    if (det > 0.0f && un >= 0.0f && vn >= 0.0f && __fadd_rn(un, vn) <= det)
+        consider(h, __fdiv_rn(__fmul_rn(c, sg), det), prim, slot);
 }
 
 // (e2 x e1 | e2.(s x e1)), (e2 x s | prim), (s x e1 | material) for origin (ox,oy,oz)
@@ -163,21 +167,39 @@ __device__ __forceinline__ void cam_tri_record(float4 v0, float4 e1, float4 e2, 
     r1.w = v0.w; r2.w = e1.w;
 }
 
-// camera route: record `slot` of the per-frame table
-__device__ __forceinline__ void test_cam_tri(const float4* __restrict__ cam_prims, int slot, const Ray& r, Hit& h) {
+// camera route: record `slot` of the per-camera table; all three loads issued up front, one combined predicate
+__device__ __forceinline__ void test_cam_tri_records(const float4& r0, const float4& r1, const float4& r2, int slot, const Ray& r, Hit& h) {
+    const float det = dot3(r.dx, r.dy, r.dz, r0.x, r0.y, r0.z);
+    const float un = dot3(r.dx, r.dy, r.dz, r1.x, r1.y, r1.z);
+    const float vn = dot3(r.dx, r.dy, r.dz, r2.x, r2.y, r2.z);
+    tri_accept(h, det, un, vn, r0.w, __float_as_int(r1.w), slot);
+}
+__device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ cam_prims, int slot, const Ray& r, Hit& h) {
     const float4* p = cam_prims + 3 * (size_t)slot;
-    float4 r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
-    tri_finish(h, r.dx, r.dy, r.dz, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r0.w, __float_as_int(r1.w), slot);
+    test_cam_tri_records(__ldg(p), __ldg(p + 1), __ldg(p + 2), slot, r, h);
 }
 
+// any-ray route
+__device__ __forceinline__ void test_tri_mt(const SceneView& sc, int slot, const Ray& r, Hit& h) {
+    const float4* p = sc.prims + 3 * (size_t)slot;
+    const float4 v0 = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
+    float px, py, pz, qx, qy, qz;
+    cross3(r.dx, r.dy, r.dz, e2.x, e2.y, e2.z, px, py, pz);
+    const float det = dot3(e1.x, e1.y, e1.z, px, py, pz);
+    const float sx = __fsub_rn(r.ox, v0.x), sy = __fsub_rn(r.oy, v0.y), sz = __fsub_rn(r.oz, v0.z);
+    const float un = dot3(sx, sy, sz, px, py, pz);
+    cross3(sx, sy, sz, e1.x, e1.y, e1.z, qx, qy, qz);
+    const float vn = dot3(r.dx, r.dy, r.dz, qx, qy, qz);
+    const float c = dot3(e2.x, e2.y, e2.z, qx, qy, qz);
+    tri_accept(h, det, un, vn, c, __float_as_int(v0.w), slot);
+}
+
+// cam: this ray is a camera ray (table route for triangles)
 template <bool TRI>
-__device__ __forceinline__ void test_prim(const SceneView& sc, int slot, const Ray& r, Hit& h) {
+__device__ __forceinline__ void test_prim(const SceneView& sc, int slot, const Ray& r, Hit& h, bool cam) {
     if (TRI) {
-        const float4* p = sc.prims + 3 * (size_t)slot;
-        float4 v0 = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
-        float4 r0, r1, r2;
-        cam_tri_record(v0, e1, e2, r.ox, r.oy, r.oz, r0, r1, r2);
-        tri_finish(h, r.dx, r.dy, r.dz, r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z, r0.w, __float_as_int(v0.w), slot);
+        if (cam) test_cam_tri_packet(sc.cam_prims, slot, r, h);
+        else test_tri_mt(sc, slot, r, h);
     } else {
         // v1 Sphere::hit in double on the float32 ray / sphere, roots rounded to float32
         float4 s = __ldg(sc.prims + slot);
@@ -208,7 +230,7 @@ constexpr int kDone = -1;
 // distance exceeds the closest hit.  (Same visiting order as oracle MODE_NEAR_FIRST, so the
 // node / primitive counters agree exactly with the CPU checker.)
 template <bool TRI, bool STATS>
-__device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit& h, Counters& cnt) {
+__device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit& h, Counters& cnt, bool cam) {
     h.t = kTMax; h.prim = -1; h.slot = -1;
     if (sc.n_nodes == 0) return;
     float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
@@ -240,7 +262,7 @@ __device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit
             const int first = code >> 3, count = code & 7;
             for (int k = 0; k < count; ++k) {
                 if (STATS) cnt.prims += 1;
-                test_prim<TRI>(sc, first + k, r, h);
+                test_prim<TRI>(sc, first + k, r, h, cam);
             }
         }
         bool found = false;
@@ -289,7 +311,7 @@ __device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Tr
 // internal node).
 template <bool TRI, bool STATS>
 __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav& tv, int* stack_code,
-                                         float* stack_tn, int min_active, int leaf_vote, Counters& cnt) {
+                                         float* stack_tn, int min_active, int leaf_vote, Counters& cnt, bool cam) {
     for (;;) {
         const bool is_int = tv.cur >= 0, is_leaf = tv.cur < kDone;
         const int n_int = __popc(__ballot_sync(0xffffffffu, is_int));
@@ -301,7 +323,7 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
                 int first = code >> 3, count = code & 7;
                 for (int k = 0; k < count; ++k) {
                     if (STATS) cnt.prims += 1;
-                    test_prim<TRI>(sc, first + k, r, tv.h);
+                    test_prim<TRI>(sc, first + k, r, tv.h, cam);
                 }
                 trav_pop(tv, stack_code, stack_tn);
             }
@@ -359,23 +381,6 @@ __device__ __forceinline__ bool box_hit_oct(const float4& lo, const float4& hi, 
     return n <= f;
 }
 
-// camera route of the triangle test for a packet: all three record loads issued up front, one
-// combined predicate (det == 0 fails `det > 0` after the sign flip), sign flip as a multiplication
-// by +-1 (exact) so that it runs on the FFMA pipe.  Same bits as test_cam_tri().
-__device__ __forceinline__ void test_cam_tri_records(const float4& r0, const float4& r1, const float4& r2, int slot, const Ray& r, Hit& h) {
-    float det = dot3(r.dx, r.dy, r.dz, r0.x, r0.y, r0.z);
-    float un = dot3(r.dx, r.dy, r.dz, r1.x, r1.y, r1.z);
-    float vn = dot3(r.dx, r.dy, r.dz, r2.x, r2.y, r2.z);
-    const float sg = det < 0.0f ? -1.0f : 1.0f;
-    det = __fmul_rn(det, sg); un = __fmul_rn(un, sg); vn = __fmul_rn(vn, sg);
-    if (det > 0.0f && un >= 0.0f && vn >= 0.0f && __fadd_rn(un, vn) <= det)
-        consider(h, __fdiv_rn(__fmul_rn(r0.w, sg), det), __float_as_int(r1.w), slot);
-}
-__device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ cam_prims, int slot, const Ray& r, Hit& h) {
-    const float4* p = cam_prims + 3 * (size_t)slot;
-    test_cam_tri_records(__ldg(p), __ldg(p + 1), __ldg(p + 2), slot, r, h);
-}
-
 template <bool TRI, bool STATS, int OCT>
 __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* __restrict__ cam_prims, const Ray& r, int lane,
                                             uint2* __restrict__ stack, int cur, Hit& h, Counters& cnt, int& work) {
@@ -410,7 +415,7 @@ __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* _
             work += count;
             for (int k = 0; k < count; ++k) {
                 if (TRI) test_cam_tri_packet(cam_prims, first + k, r, h);
-                else test_prim<false>(sc, first + k, r, h);
+                else test_prim<false>(sc, first + k, r, h, true);
             }
         }
         const unsigned max_t = __reduce_max_sync(0xffffffffu, __float_as_uint(h.t));
@@ -541,7 +546,7 @@ __device__ __forceinline__ void radiance(const SceneView& sc, const CameraBlock&
     float cr = 0.0f, cg = 0.0f, cb = 0.0f, tr = 1.0f, tg = 1.0f, tb = 1.0f;
     for (int b = 0; b < max_depth; ++b) {
         Hit h;
-        intersect<TRI, STATS>(sc, r, h, cnt);
+        intersect<TRI, STATS>(sc, r, h, cnt, b == 0);
         if (STATS) cnt.segments += 1;
         if (h.prim < 0) {
             cr = __fmaf_rn(tr, sc.bg_r, cr); cg = __fmaf_rn(tg, sc.bg_g, cg); cb = __fmaf_rn(tb, sc.bg_b, cb);

@@ -32,7 +32,7 @@ k_trace_primary(const __grid_constant__ SceneView sc, const __grid_constant__ Ca
         if (!p.active) continue;
         Ray r = camera_ray(cam, p.i, p.j, 0.5f, 0.5f, inv_w, inv_h);
         Hit h;
-        intersect<TRI, STATS>(sc, r, h, cnt);
+        intersect<TRI, STATS>(sc, r, h, cnt, true);
         d_prim[p.out_index] = h.prim;
         d_t[p.out_index] = h.prim >= 0 ? h.t : 0.0f;
         if (STATS) { rays += 1; cnt.segments += 1; }
@@ -51,7 +51,7 @@ k_trace_rays(const __grid_constant__ SceneView sc, const float* __restrict__ org
         normalize3(dx, dy, dz);
         Ray r = make_ray(org[3 * k], org[3 * k + 1], org[3 * k + 2], dx, dy, dz);
         Hit h;
-        intersect<TRI, STATS>(sc, r, h, cnt);
+        intersect<TRI, STATS>(sc, r, h, cnt, false);
         d_prim[k] = h.prim;
         d_t[k] = h.prim >= 0 ? h.t : 0.0f;
         if (STATS) { rays += 1; cnt.segments += 1; }
@@ -206,7 +206,7 @@ k_path(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
         if (act == 0u) break;                      // every lane idle and the pool is empty
         // leave the loop again once a quarter (32 - refill_below in 32) of the lanes that entered are done
         int min_active = (__popc(act) * refill_below) >> 5;
-        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, leaf_vote, cnt);
+        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, leaf_vote, cnt, b == 0);
         if (phase == PH_TRAV && tv.cur == kDone) phase = PH_SHADE;
     }
     if (STATS) flush_stats(d_stats, rays, cnt);
@@ -476,7 +476,6 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
                           uint32_t sample_offset, int resolve, float* d_out, int32_t* d_prim, float* d_t,
                           const LaunchCfg& cfg) {
     int n_work = work_items(tm);
-    if (TRI && !cfg.cam_table_valid) launch_cam_tris(sc, cam, cfg);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_packet<TRI, STATS, AOV, false>, kPacketThreads, 0);
     int grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);
@@ -531,6 +530,7 @@ cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraB
     if (n_work == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
     if (e != cudaSuccess) return e;
+    if (is_tri && !cfg.cam_table_valid && (e = launch_cam_tris(sc, cam, cfg)) != cudaSuccess) return e;   // camera rays use the table
     bool st = cfg.d_stats != nullptr;
     if (cfg.variant == 3) {
         if (is_tri) return st ? launch_packet<true, true, true>(sc, cam, tm, 1, 0, 0, 0, nullptr, d_prim, d_t, cfg)
@@ -582,6 +582,7 @@ cudaError_t launch_render(const SceneView& sc, bool is_tri, const CameraBlock& c
     if (n_work == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
     if (e != cudaSuccess) return e;
+    if (is_tri && !cfg.cam_table_valid && (e = launch_cam_tris(sc, cam, cfg)) != cudaSuccess) return e;   // bounce 0 uses the table
     bool st = cfg.d_stats != nullptr;
     if (cfg.variant == 3 && max_depth == 1) {
         if (is_tri) return st ? launch_packet<true, true, false>(sc, cam, tm, spp, seed, sample_offset, resolve, d_out, nullptr, nullptr, cfg)

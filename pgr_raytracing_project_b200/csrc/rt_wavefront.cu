@@ -173,7 +173,7 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
             continue;                               // root misses waiting to be published / more to fetch
         }
         int min_active = pool_empty ? 1 : (__popc(act) * refill_below) >> 5;
-        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, leaf_vote, cnt);
+        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, leaf_vote, cnt, bounce == 0);
     }
     if (STATS) flush_stats(d_stats, 0, cnt);
 }
@@ -266,7 +266,7 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
                           int integrator, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out,
                           int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb, int* n_launches) {
     const bool packet0 = !AOV && cfg.variant == 4;             // bounce 0 by camera-ray packets
-    if (packet0 && TRI && !cfg.cam_table_valid) {
+    if (TRI && !cfg.cam_table_valid) {                         // bounce 0 (camera rays) reads the camera-relative table
         cudaError_t e = launch_cam_tris(sc, cam, cfg);
         if (e != cudaSuccess) return e;
         *n_launches += 1;

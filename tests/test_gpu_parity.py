@@ -217,6 +217,20 @@ def test_scene_container_with_cached_bvh(ctx, tmp_path):
     assert np.array_equal(ctx.render(W, H, 2, 3, seed=4).cpu().numpy(), img)
 
 
+def test_trace_rays_triangles_bit_exact(ctx):
+    """Arbitrary (incoherent) rays over a triangle scene take the any-ray triangle route on both sides."""
+    s = scenes.random_triangles(30_000, seed=14)
+    _setup(ctx, s, 64, 64)
+    rng = np.random.default_rng(6)
+    n = 20_000
+    org = rng.uniform(-12, 12, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    rp, rt = [x.cpu().numpy() for x in ctx.trace_rays(org, d)]
+    o = _oracle_for(ctx, s, s.camera.as_array(1.0))
+    op, ot, _ = o.trace_rays(org, d)
+    assert np.array_equal(rp, op) and np.array_equal(rt, ot) and (rp >= 0).mean() > 0.3
+
+
 def test_empty_scene(ctx):
     ctx.set_spheres(np.zeros((0, 4), np.float32), np.zeros((0, 8), np.float32))
     ctx.set_background((0.25, 0.5, 1.0))
