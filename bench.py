@@ -430,7 +430,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 112, "d2h_bytes_per_step": W * H * 3 * 4,
                     "ms_per_step": float(e2e_t.item()) / args.steps * 1e3,
-                    "api": "rt_set_camera + rt_render_host (pinned host framebuffer)" if world == 1 else
+                    "api": "rt_set_camera + rt_render_host (pinned host framebuffer; the kernel pushes finished tiles into it)" if world == 1 else
                            "DistributedRenderer.render + copy of the resolved frame to pinned host memory on rank 0"},
             "gpu_launches": int(n_launch.item()),
             "roofline": {

@@ -156,9 +156,10 @@ int rt_resolve_planes(rt_ctx* ctx, const float* d_planes, int n_planes, int64_t 
 /* Scatter gathered compact tile buffers [rank][k][tile_h][tile_w][3] back into a H*W*3 frame. */
 int rt_untile(rt_ctx* ctx, int width, int height, int tile_w, int tile_h, int n_ranks,
               const float* d_tiles, float* d_frame, void* stream);
-/* Host-buffer convenience used by the reference-facing plugin call: render into a context-owned
- * device framebuffer and copy it to h_out (H*W*3 floats; pinned memory makes the copy async-fast).
- * Synchronous: returns when h_out is complete. */
+/* Host-buffer call behind the reference-facing RayTracer::render (old/raytracer_core copy.cpp:257, result in
+ * host memory): render into a context-owned device framebuffer and bring it to h_out (H*W*3 floats).  With
+ * page-locked h_out (cudaHostAlloc / cudaHostRegister / torch pin_memory) a camera-ray frame crosses PCIe WHILE it
+ * is rendered (option "overlap"); pageable memory works, slower.  Synchronous: returns when h_out is complete. */
 int rt_render_host(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed,
                    uint32_t sample_offset, float* h_out);
 
@@ -191,8 +192,10 @@ int rt_display_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
  * 8); "leaf_vote" 1..32 = lanes holding a leaf at which the warp runs the leaf step (default 8);
  * "builder" 0/1 = what the implicit build of the first render after a scene upload uses (rt_build_bvh's
  * argument; default 0); "schedule" 0/1 = cost-aware work order of the packet kernel (default 1);
- * "overlap" 0/1 = rt_render_host copies finished bands of a camera-ray frame to the host while the
- * kernel renders the rest (default 1). */
+ * "overlap" = how rt_render_host moves a camera-ray frame (max_depth 1, 1 spp) to the host: 2 (default) = TILE
+ * PUSH, the render kernel itself stores every finished 32x32 tile into h_out (needs page-locked, 16-byte aligned
+ * h_out; otherwise mode 1 is used), 1 = finished regions are copied by the DMA engine while the kernel renders the
+ * rest, 0 = render, then one copy. */
 int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);
 int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value);
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);   /* synchronises the device */

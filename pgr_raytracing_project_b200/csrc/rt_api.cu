@@ -89,7 +89,9 @@ struct rt_ctx {
     unsigned int* d_band_cnt = nullptr;
     unsigned int* h_band_flags = nullptr;    // cudaHostAlloc mapped
     unsigned int* d_band_flags = nullptr;    // device alias of h_band_flags
-    int overlap = 1;                         // option "overlap"
+    int overlap = 2;                         // option "overlap": 0 render then copy, 1 region flags + DMA copies, 2 tile push
+    unsigned int* d_tile_cnt = nullptr;      // tile push: one completion counter per 32x32 tile
+    int tile_cnt_cap = 0;
     // cost-aware chunk order of the packet kernel (ChunkSchedule): history of the last frame of this tile map
     int* d_chunk_order = nullptr;
     unsigned int* d_chunk_cost = nullptr;
@@ -304,7 +306,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
     cfg.d_cam_prims = c->d_cam_prims;
     cfg.d_planes = nullptr; cfg.plane_batch = 0;
     cfg.cam_table_valid = 0;
-    cfg.band = BandSignal{nullptr, nullptr, 0, 0, 1, 1, 1};
+    cfg.band = BandSignal{nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 1, 1};
     cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr, 0};
     cfg.d_block_times = c->stats ? c->d_block_times : nullptr;
     cfg.refill_below = c->refill;
@@ -349,7 +351,7 @@ int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm, const Camera
         ctx->chunk_cap = n_chunks;
     }
     long long key = ((((long long)tm.width * 65537 + tm.height) * 257 + tm.tile_w) * 257 + tm.tile_h) * 1031 + tm.first_tile;
-    key = key * 1031 + tm.tile_stride + 7919LL * tm.compact + 104729LL * tm.n_local_tiles + 15485863LL * tm.skew + (cfg.band.cnt != nullptr ? 32452843LL : 0LL) + 49979687LL * items_per_block;
+    key = key * 1031 + tm.tile_stride + 7919LL * tm.compact + 104729LL * tm.n_local_tiles + 15485863LL * tm.skew + (cfg.band.cnt != nullptr ? 32452843LL : 0LL) + (cfg.band.host_fb != nullptr ? 86028121LL : 0LL) + 49979687LL * items_per_block;
     // the order is rebuilt (k_chunk_order, ~12 us) for a new tile map, whenever the camera has changed since it was
     // built, on the 2nd frame (first one with costs) and then every 8th frame; in between the costs accumulate
     const bool new_map = key != ctx->chunk_key;
@@ -449,7 +451,7 @@ void rt_destroy(rt_ctx* ctx) {
         free_device_scene(ctx);
         free_wave(ctx);
         cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick); cudaFree(ctx->d_display); cudaFree(ctx->d_planes);
-        cudaFree(ctx->d_band_cnt); cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
+        cudaFree(ctx->d_band_cnt); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
         if (ctx->h_band_flags) cudaFreeHost(ctx->h_band_flags);
         if (ctx->render_stream) cudaStreamDestroy(ctx->render_stream);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -910,8 +912,8 @@ constexpr int kMaxBands = 64;
 // cudaMemcpy2DAsync on a second stream as soon as the kernel raises the region's flag.
 static int render_host_overlapped(rt_ctx* ctx, int width, int height, int spp, uint64_t seed, uint32_t sample_offset,
                                   float* h_out) {
-    if (!ctx->render_stream) {
-        CK(cudaStreamCreateWithFlags(&ctx->render_stream, cudaStreamNonBlocking));
+    if (!ctx->render_stream) CK(cudaStreamCreateWithFlags(&ctx->render_stream, cudaStreamNonBlocking));
+    if (!ctx->copy_stream) {
         CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         CK(cudaMalloc(&ctx->d_band_cnt, kMaxBands * sizeof(unsigned int)));
         CK(cudaHostAlloc(&ctx->h_band_flags, kMaxBands * sizeof(unsigned int), cudaHostAllocMapped));
@@ -974,6 +976,62 @@ static int render_host_overlapped(rt_ctx* ctx, int width, int height, int spp, u
     return 0;
 }
 
+// Single-launch render whose kernel stores every finished 32x32 tile straight into the caller's page-locked frame
+// (BandSignal tile push, rt_kernels.h): no polling, no DMA; returns when the stream has drained.
+// d_host = device alias of h_out.
+static int render_host_push(rt_ctx* ctx, int width, int height, int spp, uint64_t seed, uint32_t sample_offset, float* d_host) {
+    if (!ctx->render_stream) CK(cudaStreamCreateWithFlags(&ctx->render_stream, cudaStreamNonBlocking));
+    ctx->aspect = (double)width / height;
+    CameraBlock cam = camera_block(ctx, ctx->aspect);
+    TileMap tm = full_frame_map(width, height);
+    if (tm.n_tiles > ctx->tile_cnt_cap) {
+        cudaFree(ctx->d_tile_cnt); ctx->d_tile_cnt = nullptr; ctx->tile_cnt_cap = 0;
+        CK(cudaMalloc(&ctx->d_tile_cnt, (size_t)tm.n_tiles * sizeof(unsigned int)));
+        ctx->tile_cnt_cap = tm.n_tiles;
+    }
+    LaunchCfg cfg = launch_cfg(ctx, ctx->render_stream, 1);
+    BandSignal& bs = cfg.band;
+    bs.cnt = ctx->d_tile_cnt; bs.flags = nullptr; bs.host_fb = d_host;
+    static const char* times_path = std::getenv("B200RT_PUSH_TIMES");
+    static unsigned long long* d_times = nullptr;
+    if (times_path) {
+        if (!d_times) CK(cudaMalloc(&d_times, (size_t)1 << 20));
+        CK(cudaMemsetAsync(d_times, 0, (size_t)tm.n_tiles * 8, ctx->render_stream));
+        bs.push_times = d_times;
+    }
+    bs.tiles_x = tm.tiles_x; bs.tiles_y = tm.n_tiles / tm.tiles_x;
+    bs.band_rows = 1; bs.group_cols = 1; bs.n_groups = tm.tiles_x;          // one region per tile, raster due order
+    if (int rc = attach_schedule(ctx, cfg, tm, cam)) return rc;
+    claim_cam_table(ctx, cfg, cam);
+    const auto t0 = std::chrono::steady_clock::now();
+    CK(cudaMemsetAsync(ctx->d_tile_cnt, 0, (size_t)tm.n_tiles * sizeof(unsigned int), ctx->render_stream));
+    CK(launch_render(scene_view(ctx), ctx->is_tri, cam, tm, spp, 1, ctx->integrator, seed, sample_offset, 1, ctx->d_fb, cfg));
+    ctx->launches += render_launches(ctx, cfg);
+    CK(cudaStreamSynchronize(ctx->render_stream));
+    if (times_path) {                                                        // debug dump: tile, ns since the first push
+        std::vector<unsigned long long> t((size_t)tm.n_tiles);
+        cudaMemcpy(t.data(), d_times, t.size() * 8, cudaMemcpyDeviceToHost);
+        if (FILE* f = std::fopen(times_path, "w")) {
+            unsigned long long t_min = ~0ull;
+            for (auto v : t) if (v && v < t_min) t_min = v;
+            for (size_t k = 0; k < t.size(); ++k) std::fprintf(f, "%zu %lld\n", k, t[k] ? (long long)(t[k] - t_min) : -1ll);
+            std::fclose(f);
+        }
+    }
+    static const bool trace = std::getenv("B200RT_TRACE") != nullptr;
+    if (trace) std::fprintf(stderr, "tile push: launch..drain %.0f us\n", std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+    return 0;
+}
+
+// device alias of a page-locked host buffer the SMs can store into with 16-byte vectors, or nullptr
+static float* pushable_alias(float* h_out) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h_out) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || at.devicePointer == nullptr) return nullptr;
+    if (((uintptr_t)at.devicePointer & 15u) != 0) return nullptr;
+    return static_cast<float*>(at.devicePointer);
+}
+
 int rt_render_host(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,
                    float* h_out) {
     if (!ctx) return 1;
@@ -991,6 +1049,8 @@ int rt_render_host(rt_ctx* ctx, int width, int height, int spp, int max_depth, u
     if (int rc = ensure_device(ctx)) return rc;
     if (ctx->overlap && pick_kernel(ctx, max_depth) == 3 && max_depth == 1 && spp == 1 && ctx->n > 0 && need >= ((size_t)1 << 18)) {
         CK(cudaStreamSynchronize(nullptr));               // order after earlier work of the legacy stream
+        if (ctx->overlap >= 2)
+            if (float* alias = pushable_alias(h_out)) return render_host_push(ctx, width, height, spp, seed, sample_offset, alias);
         return render_host_overlapped(ctx, width, height, spp, seed, sample_offset, h_out);
     }
     if (int rc = rt_render(ctx, width, height, spp, max_depth, seed, sample_offset, ctx->d_fb, nullptr)) return rc;
@@ -1044,7 +1104,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "stats") ctx->stats = value != 0;
     else if (k == "kernel") { if (value < -1 || value > 4) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront), 3 (camera-ray packets) or 4 (wavefront with packet bounce 0)"); ctx->kernel = (int)value; }
     else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
-    else if (k == "overlap") ctx->overlap = value != 0;
+    else if (k == "overlap") { if (value < 0 || value > 2) return fail(ctx, "overlap must be 0 (render, then copy), 1 (region flags + DMA copies) or 2 (tile push)"); ctx->overlap = (int)value; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail(ctx, "builder must be 0 (reference median split, host) or 1 (LBVH, device)"); ctx->builder = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
     else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);

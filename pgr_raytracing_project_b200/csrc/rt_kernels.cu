@@ -291,6 +291,29 @@ k_chunk_order(unsigned int* __restrict__ cost_sum, unsigned int* __restrict__ co
     for (int k = tid; k < n; k += 1024) { cost_sum[k] = 0u; cost_max[k] = 0u; }
 }
 
+// Tile push (BandSignal::host_fb): one warp copies the finished 32x32-pixel tile (ty, tx) of the device frame `fb`
+// into the caller's page-locked frame `host` (its device alias): rows of 384 contiguous bytes, read from L2 (other
+// SMs wrote them), 16 bytes per lane when the row pitch allows it.  Kept out of line: k_packet's register budget.
+__device__ __noinline__ void push_tile(const float* __restrict__ fb, float* __restrict__ host, int width, int height, int ty,
+                                       int tx, int lane) {
+    const int x0 = tx * 32, y0 = ty * 32;
+    const int rows = min(32, height - y0), cols = min(32, width - x0);
+    const size_t base = ((size_t)y0 * width + x0) * 3;
+    if (cols == 32 && (width & 3) == 0) {
+        const size_t pitch4 = (size_t)width * 3 / 4;
+        const float4* s = reinterpret_cast<const float4*>(fb + base) + lane;
+        float4* d = reinterpret_cast<float4*>(host + base) + lane;
+        if (lane < 24) {
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) d[(size_t)r * pitch4] = __ldcg(s + (size_t)r * pitch4);
+        }
+    } else {
+        const size_t pitch = (size_t)width * 3;
+        for (int r = 0; r < rows; ++r)
+            for (int k = lane; k < cols * 3; k += 32) host[base + (size_t)r * pitch + k] = __ldcg(fb + base + (size_t)r * pitch + k);
+    }
+}
+
 // ptxas settles at 48 registers = 5 CTAs of 256 threads per SM, the measured optimum: forcing 40 / 32 registers (6 / 8
 // CTAs) spills and is 3 % / 18 % slower, and anything that pushes the kernel to 64 registers (4 CTAs) costs 4-5 % --
 // which is why the final pixel store here is the plain one and not warp_store_rgb
@@ -375,9 +398,24 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
         if (!AOV && !item_mode && band.cnt != nullptr) {     // see BandSignal
             __threadfence();                                 // release: this block's pixels before the count
             __syncwarp();
-            if (lane == 0) {
-                const int b = region_of_tile(band, w >> 5);
-                if (atomicAdd(band.cnt + b, 1u) + 1u == (unsigned)region_blocks(band, b)) { __threadfence_system(); band.flags[b] = 1u; }
+            if (band.host_fb == nullptr) {
+                if (lane == 0) {
+                    const int b = region_of_tile(band, w >> 5);
+                    if (atomicAdd(band.cnt + b, 1u) + 1u == (unsigned)region_blocks(band, b)) { __threadfence_system(); band.flags[b] = 1u; }
+                }
+            } else {                                         // tile push: regions are tiles (32 blocks each)
+                const int tile = w >> 5;
+                unsigned last = 0u;
+                if (lane == 0) last = atomicAdd(band.cnt + tile, 1u) + 1u == 32u ? 1u : 0u;
+                if (__shfl_sync(0xffffffffu, last, 0)) {
+                    __threadfence();                         // acquire: the other 31 blocks' pixels
+                    push_tile(d_out, band.host_fb, tm.width, tm.height, tile / band.tiles_x, tile % band.tiles_x, lane);
+                    if (band.push_times != nullptr && lane == 0) {
+                        unsigned long long t;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                        band.push_times[tile] = t;
+                    }
+                }
             }
         }
     }

@@ -31,9 +31,17 @@ struct TileMap {
 // frame.  Regions rather than full-width bands, because a frame has a few very slow packets (see
 // ChunkSchedule) and a band that contains one cannot complete before it does; small regions confine
 // the wait to a small share of the bytes.
+//
+// TILE PUSH (host_fb != nullptr; regions are single 32x32 tiles): no flags, no host polling, no DMA -- the warp that
+// completes a tile reads its 32 rows back from L2 and stores them straight into the caller's page-locked frame
+// (host_fb = that buffer's device alias), 16 bytes per lane, 384 contiguous bytes per row.  SM-issued coalesced
+// stores into mapped host memory run at 51.5 GB/s on this box (DMA: 56.5; tools/exp/zc_copy.cu), so the frame
+// crosses PCIe WHILE it is rendered and the call ends one tile (12 KB) after the kernel's last block.
 struct BandSignal {
     unsigned int* cnt;               // device, one counter per region, zeroed on the launch stream
     volatile unsigned int* flags;    // mapped pinned host memory (device pointer), zeroed by the host
+    float* host_fb;                  // tile push: device alias of the caller's page-locked H x W x 3 frame, else nullptr
+    unsigned long long* push_times;  // debug (B200RT_PUSH_TIMES): globaltimer when a tile's push has been issued, or nullptr
     int tiles_x, tiles_y;            // tile grid of the frame (full-frame tile map only)
     int band_rows, group_cols;       // region size in tiles
     int n_groups;                    // regions per band row

@@ -359,22 +359,29 @@ def test_resolve_planes_is_the_ordered_sum(ctx):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("W,H", [(640, 480), (1000, 333)])
+@pytest.mark.parametrize("W,H", [(640, 480), (1000, 333), (1002, 335), (1920, 1080)])
 def test_render_host_matches_device_render(ctx, W, H):
-    """rt_render_host (host buffer; for camera-ray frames the device->host copy of finished bands overlaps
-    the rest of the render) returns exactly the frame rt_render leaves on the device, pinned or pageable."""
+    """rt_render_host (host buffer) returns exactly the frame rt_render leaves on the device, pinned or pageable,
+    in every overlap mode: 2 = the kernel pushes finished 32x32 tiles straight into the page-locked frame (camera-ray
+    frames: depth 1, 1 spp; full tiles, partial tiles at the right / bottom edge, row pitch not a multiple of 16 B),
+    1 = region flags + DMA copies, 0 = render, then copy."""
     import torch
     s = scenes.random_triangles(30_000, seed=21)
     _setup(ctx, s, W, H)
-    for depth, spp in [(1, 2), (3, 1)]:
+    for depth, spp in [(1, 1), (1, 2), (3, 1)]:
         dev = ctx.render(W, H, spp, depth, seed=77, sample_offset=3).cpu().numpy()
         pinned = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
-        for overlap in (1, 0):
+        for overlap in (2, 1, 0, 2):
             ctx.set_option("overlap", overlap)
             pinned.zero_()
             ctx.render_host(W, H, spp, depth, seed=77, sample_offset=3, out=pinned.numpy())
-            assert np.array_equal(pinned.numpy(), dev)
-        ctx.set_option("overlap", 1)
+            assert np.array_equal(pinned.numpy(), dev), (depth, spp, overlap)
+        # a view into a larger page-locked buffer at an offset that is not 16-byte aligned: falls back to mode 1
+        big = torch.empty(H * W * 3 + 8, dtype=torch.float32, pin_memory=True)
+        view = big[1:1 + H * W * 3].view(H, W, 3)
+        view.zero_()
+        ctx.render_host(W, H, spp, depth, seed=77, sample_offset=3, out=view.numpy())
+        assert np.array_equal(view.numpy(), dev)
         pageable = ctx.render_host(W, H, spp, depth, seed=77, sample_offset=3)
         assert np.array_equal(pageable, dev)
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Experiment (GPU box): framebuffer written straight into pinned host memory by the kernel vs render + D2H copy."""
-import ctypes as C
+"""Experiment (GPU box): rt_render_host in its three overlap modes (2 = the kernel pushes finished tiles into the
+page-locked frame, 1 = region flags + DMA copies, 0 = render, then copy) on the C3 frame; host clock."""
 import os
 import sys
 import time
@@ -19,30 +19,16 @@ ctx.set_camera(s.camera.position, s.camera.target, s.camera.up, s.camera.fov)
 dev = torch.empty((H, W, 3), device=ctx.device)
 host = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
 ref = ctx.render(W, H, 1, 1, seed=1, out=dev).cpu()
-
-
-def zero_copy():
-    ctx._ck(ctx.L.rt_render(ctx.h, W, H, 1, 1, C.c_uint64(1), C.c_uint32(0), host.data_ptr(), ctx._stream()))
-    torch.cuda.synchronize()
-
-
-def copy():
-    ctx.render(W, H, 1, 1, seed=1, out=dev)
-    host.copy_(dev, non_blocking=True)
-    torch.cuda.synchronize()
-
-
-def only_copy():
-    host.copy_(dev, non_blocking=True)
-    torch.cuda.synchronize()
-
-
-for name, fn in [("render+copy", copy), ("copy only", only_copy), ("render_host", lambda: ctx.render_host(W, H, 1, 1, seed=1, out=host.numpy()))]:
-    for _ in range(3):
-        fn()
-    t0 = time.perf_counter()
-    for _ in range(20):
-        fn()
-    dt = (time.perf_counter() - t0) / 20
-    ok = bool(torch.equal(host, ref)) if name != "copy only" else True
-    print(f"{name:12s} {dt * 1e3:.3f} ms/frame  same={ok}", flush=True)
+flush = torch.empty(512 << 20, dtype=torch.uint8, device=ctx.device)
+for mode, sched in ((2, 1), (1, 1), (0, 1), (2, 0), (2, 1)):
+    ctx.set_option("overlap", mode)
+    ctx.set_option("schedule", sched)
+    for _ in range(5):
+        ctx.render_host(W, H, 1, 1, seed=1, out=host.numpy())
+    ts = []
+    for _ in range(30):
+        flush.zero_(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ctx.render_host(W, H, 1, 1, seed=1, out=host.numpy())
+        ts.append(time.perf_counter() - t0)
+    print(f"overlap={mode} schedule={sched}: median {np.median(ts) * 1e3:.3f} ms  min {min(ts) * 1e3:.3f}  same={bool(torch.equal(host, ref))}", flush=True)
