@@ -200,7 +200,7 @@ int ensure_device(rt_ctx* ctx) {
     const int64_t n = ctx->n;
     const int64_t n_nodes = (int64_t)ctx->nodes.size();
     if (n > 0) {
-        const int per = ctx->is_tri ? 3 : 1;
+        const int per = ctx->is_tri ? kTriStride : 1;
         std::vector<float4> prims((size_t)n * per);
         for (int64_t slot = 0; slot < n; ++slot) {
             const int32_t p = ctx->prim_index[slot];
@@ -209,9 +209,9 @@ int ensure_device(rt_ctx* ctx) {
                 int32_t mid = ctx->mat_id[p];
                 float pw, mw;
                 std::memcpy(&pw, &p, 4); std::memcpy(&mw, &mid, 4);
-                prims[3 * slot + 0] = make_float4(v[0], v[1], v[2], pw);
-                prims[3 * slot + 1] = make_float4(v[3] - v[0], v[4] - v[1], v[5] - v[2], mw);   // e1 = v1 - v0
-                prims[3 * slot + 2] = make_float4(v[6] - v[0], v[7] - v[1], v[8] - v[2], 0.0f); // e2 = v2 - v0
+                prims[kTriStride * slot + 0] = make_float4(v[0], v[1], v[2], pw);
+                prims[kTriStride * slot + 1] = make_float4(v[3] - v[0], v[4] - v[1], v[5] - v[2], mw);   // e1 = v1 - v0
+                prims[kTriStride * slot + 2] = make_float4(v[6] - v[0], v[7] - v[1], v[8] - v[2], 0.0f); // e2 = v2 - v0
             } else {
                 const float* s = &ctx->prim_data[4 * (size_t)p];
                 prims[slot] = make_float4(s[0], s[1], s[2], s[3]);
@@ -219,7 +219,7 @@ int ensure_device(rt_ctx* ctx) {
         }
         CK(cudaMalloc(&ctx->d_prims, prims.size() * sizeof(float4)));
         CK(cudaMemcpy(ctx->d_prims, prims.data(), prims.size() * sizeof(float4), cudaMemcpyHostToDevice));
-        if (ctx->is_tri) CK(cudaMalloc(&ctx->d_cam_prims, prims.size() * sizeof(float4)));
+        if (ctx->is_tri) CK(cudaMalloc(&ctx->d_cam_prims, (size_t)n * 3 * sizeof(float4)));
         CK(cudaMalloc(&ctx->d_slot_prim, (size_t)n * sizeof(int)));
         CK(cudaMemcpy(ctx->d_slot_prim, ctx->prim_index.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
         // device node = bmin | code, bmax | 0: code >= 0 child-pair index, code <= -2 leaf ~((first << 3) | count)

@@ -24,6 +24,8 @@ namespace b200rt {
 constexpr float kTMin = 0.001f;   // old/raytracer_core copy.cpp:217
 constexpr float kTMax = 1e10f;
 constexpr int kStackDepth = 64;   // cpp_raytracer/raytracer_core.cpp:200
+constexpr int kTriStride = 3;     // float4 per triangle record: v0|prim, e1|material, e2|0 (48 B).  Measured and dropped: 64-byte
+                                  // records read as two 256-bit loads (7.82 vs 7.78 ms on the C3 4-spp depth-4 frame, +33 % bytes)
 
 struct CameraBlock {              // basis in double: primary directions are rounded to f32 once
     float px, py, pz;
@@ -34,7 +36,7 @@ struct CameraBlock {              // basis in double: primary directions are rou
 
 struct SceneView {
     const float4* __restrict__ nodes;      // 2 x float4 per 32-byte node: bmin | code, bmax | 0 (see intersect())
-    const float4* __restrict__ prims;      // leaf order; triangle: v0|prim, e1|material, e2|0 ; sphere: c|r
+    const float4* __restrict__ prims;      // leaf order; triangle: v0|prim, e1|material, e2|0 (kTriStride x float4) ; sphere: c|r
     const float4* __restrict__ cam_prims;  // triangles: camera-relative records for the current camera position (k_cam_tris)
     const int* __restrict__ slot_prim;     // slot -> primitive number (upload order)
     const float4* __restrict__ mats;       // 2 x float4 per material: albedo|metallic, roughness|emission
@@ -117,6 +119,19 @@ __device__ __forceinline__ Ray camera_ray(const CameraBlock& c, int i, int j, fl
 // ------------------------------------------------------------------------------- intersection
 struct Hit { float t; int prim; int slot; };
 
+// A sibling pair (64 bytes, 64-byte aligned) as TWO 256-bit loads (LDG.E.256.CONSTANT, sm_100: ld.global.nc.v8.f32)
+// instead of four 128-bit ones.  The per-lane traversal of incoherent rays is bound by the L1TEX tag stage: every
+// load instruction costs one pass per DISTINCT 128-byte line among the lanes, however many bytes each lane takes
+// from its line, so halving the instructions halves the passes (ncu: l1tex__throughput 87 % with 4 x LDG.128).
+__device__ __forceinline__ void ldg_node(const float4* __restrict__ p, float4& lo, float4& hi) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
+}
+__device__ __forceinline__ void ldg_pair(const float4* __restrict__ p, float4& l0, float4& l1, float4& r0, float4& r1) {
+    ldg_node(p, l0, l1);
+    ldg_node(p + 2, r0, r1);
+}
+
 __device__ __forceinline__ bool box_hit(const float4& lo, const float4& hi, const Ray& r, float tlo,
                                         float thi, float& tn) {
     float x1 = __fmaf_rn(lo.x, r.ix, -r.ax), x2 = __fmaf_rn(hi.x, r.ix, -r.ax);
@@ -181,7 +196,7 @@ __device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ c
 
 // any-ray route
 __device__ __forceinline__ void test_tri_mt(const SceneView& sc, int slot, const Ray& r, Hit& h) {
-    const float4* p = sc.prims + 3 * (size_t)slot;
+    const float4* p = sc.prims + kTriStride * (size_t)slot;
     const float4 v0 = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
     float px, py, pz, qx, qy, qz;
     cross3(r.dx, r.dy, r.dz, e2.x, e2.y, e2.z, px, py, pz);
@@ -244,7 +259,8 @@ __device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit
     for (;;) {
         if (cur >= 0) {
             const float4* p = sc.nodes + 2 * (size_t)cur;
-            float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
+            float4 l0, l1, r0, r1;
+            ldg_pair(p, l0, l1, r0, r1);
             if (STATS) cnt.nodes += 2;
             float tl, tr;
             bool hl = box_hit(l0, l1, r, kTMin, h.t, tl);
@@ -282,10 +298,38 @@ __device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit
 
 struct Trav { int cur; int sp; Hit h; };
 
-__device__ __forceinline__ void trav_pop(Trav& tv, const int* stack_code, const float* stack_tn) {
+// Per-lane traversal stacks.  LocalStack: 64 entries of local memory (two word-interleaved arrays).  HybridStack<D>:
+// the first D levels live in SHARED memory (uint2 entry, [level][thread]: conflict-free whatever level each lane is
+// at), deeper levels fall back to local memory.  Local-memory stack traffic goes through the L1 tag stage like any
+// global access -- in the incoherent-bounce kernel it was 18 % of all L1 sectors at a 32 % hit rate (the stack
+// lines and the node lines evict each other), and every pop sits on the ray's critical path -- shared memory has
+// neither problem.
+struct LocalStack {
+    int* code; float* tn;
+    __device__ __forceinline__ void put(int i, int c, float t) const { code[i] = c; tn[i] = t; }
+    __device__ __forceinline__ void get(int i, int& c, float& t) const { t = tn[i]; c = code[i]; }
+};
+template <int D, int THREADS>
+struct HybridStack {
+    uint2* s;                      // &smem[0][threadIdx.x]; level stride = THREADS entries
+    int* code; float* tn;          // levels >= D
+    __device__ __forceinline__ void put(int i, int c, float t) const {
+        if (i < D) s[i * THREADS] = make_uint2((unsigned)c, __float_as_uint(t));
+        else { code[i - D] = c; tn[i - D] = t; }
+    }
+    __device__ __forceinline__ void get(int i, int& c, float& t) const {
+        if (i < D) { const uint2 e = s[i * THREADS]; c = (int)e.x; t = __uint_as_float(e.y); }
+        else { t = tn[i - D]; c = code[i - D]; }
+    }
+};
+
+template <class STACK>
+__device__ __forceinline__ void trav_pop(Trav& tv, const STACK& st) {
     while (tv.sp > 0) {
         --tv.sp;
-        if (stack_tn[tv.sp] <= tv.h.t) { tv.cur = stack_code[tv.sp]; return; }
+        int c; float t;
+        st.get(tv.sp, c, t);
+        if (t <= tv.h.t) { tv.cur = c; return; }
     }
     tv.cur = kDone;
 }
@@ -309,10 +353,17 @@ __device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Tr
 // the per-ray visiting order, and with it every counter, stays exactly intersect()'s.
 // leaf_vote: the leaf phase runs when at least that many lanes hold a leaf (or no lane holds an
 // internal node).
-template <bool TRI, bool STATS>
-__device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav& tv, int* stack_code,
-                                         float* stack_tn, int min_active, int leaf_vote, Counters& cnt, bool cam) {
+// A lane that has finished a leaf, or whose internal step found no child to enter, does not pop on the spot: it
+// parks in state kNeedPop and all such lanes pop TOGETHER at the top of the next iteration (one convergent copy
+// of the pop loop instead of two divergent ones that ran for 1-4 lanes at a time: -11 % instructions).
+// CAM: 0 = no ray of this warp is a camera ray, 1 = all are, 2 = per lane (`cam`).
+constexpr int kNeedPop = (int)0x80000000;   // not a leaf code: would mean first slot 2^28 - 1, count 7
+
+template <bool TRI, bool STATS, int CAM, class STACK>
+__device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav& tv, const STACK& st, int min_active,
+                                         int leaf_vote, Counters& cnt, bool cam) {
     for (;;) {
+        if (tv.cur == kNeedPop) trav_pop(tv, st);
         const bool is_int = tv.cur >= 0, is_leaf = tv.cur < kDone;
         const int n_int = __popc(__ballot_sync(0xffffffffu, is_int));
         const int n_leaf = __popc(__ballot_sync(0xffffffffu, is_leaf));
@@ -323,13 +374,14 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
                 int first = code >> 3, count = code & 7;
                 for (int k = 0; k < count; ++k) {
                     if (STATS) cnt.prims += 1;
-                    test_prim<TRI>(sc, first + k, r, tv.h, cam);
+                    test_prim<TRI>(sc, first + k, r, tv.h, CAM == 2 ? cam : CAM == 1);
                 }
-                trav_pop(tv, stack_code, stack_tn);
+                tv.cur = kNeedPop;
             }
         } else if (is_int) {
             const float4* p = sc.nodes + 2 * (size_t)tv.cur;
-            float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
+            float4 l0, l1, r0, r1;
+            ldg_pair(p, l0, l1, r0, r1);
             if (STATS) cnt.nodes += 2;
             float tl, tr;
             bool hl = box_hit(l0, l1, r, kTMin, tv.h.t, tl);
@@ -338,11 +390,9 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
             int rc = __float_as_int(r0.w);
             if (hl && hr) {
                 if (tr < tl) { int c = lc; lc = rc; rc = c; float tf = tl; tl = tr; tr = tf; }
-                stack_code[tv.sp] = rc; stack_tn[tv.sp] = tr; ++tv.sp;
+                st.put(tv.sp, rc, tr); ++tv.sp;
                 tv.cur = lc;
-            } else if (hl) tv.cur = lc;
-            else if (hr) tv.cur = rc;
-            else trav_pop(tv, stack_code, stack_tn);
+            } else tv.cur = hl ? lc : (hr ? rc : kNeedPop);
         }
     }
 }
@@ -388,7 +438,8 @@ __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* _
     for (;;) {
         if (cur >= 0) {
             const float4* p = sc.nodes + 2 * (size_t)cur;
-            const float4 l0 = __ldg(p), l1 = __ldg(p + 1), r0 = __ldg(p + 2), r1 = __ldg(p + 3);
+            float4 l0, l1, r0, r1;
+            ldg_pair(p, l0, l1, r0, r1);
             if (STATS && lane == 0) cnt.nodes += 2;
             work += 1;
             float tl, tr;
@@ -465,7 +516,7 @@ template <bool TRI>
 __device__ __forceinline__ void shading_normal(const SceneView& sc, const Hit& h, const Ray& r, float px,
                                                float py, float pz, float& nx, float& ny, float& nz) {
     if (TRI) {
-        const float4* p = sc.prims + 3 * (size_t)h.slot;
+        const float4* p = sc.prims + kTriStride * (size_t)h.slot;
         float4 e1 = __ldg(p + 1), e2 = __ldg(p + 2);
         cross3(e1.x, e1.y, e1.z, e2.x, e2.y, e2.z, nx, ny, nz);
         normalize3(nx, ny, nz);
@@ -531,7 +582,7 @@ __device__ __forceinline__ bool scatter(const SceneView& sc, const Hit& h, Ray& 
 
 template <bool TRI>
 __device__ __forceinline__ int material_row(const SceneView& sc, const Hit& h) {
-    if (TRI) return __float_as_int(__ldg(sc.prims + 3 * (size_t)h.slot + 1).w);
+    if (TRI) return __float_as_int(__ldg(sc.prims + kTriStride * (size_t)h.slot + 1).w);
     return h.prim;
 }
 

@@ -206,7 +206,7 @@ k_path(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
         if (act == 0u) break;                      // every lane idle and the pool is empty
         // leave the loop again once a quarter (32 - refill_below in 32) of the lanes that entered are done
         int min_active = (__popc(act) * refill_below) >> 5;
-        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, leaf_vote, cnt, b == 0);
+        trav_run<TRI, STATS, 2>(sc, r, tv, LocalStack{stack_code, stack_tn}, min_active < 1 ? 1 : min_active, leaf_vote, cnt, b == 0);
         if (phase == PH_TRAV && tv.cur == kDone) phase = PH_SHADE;
     }
     if (STATS) flush_stats(d_stats, rays, cnt);
@@ -218,7 +218,7 @@ k_path(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
 __global__ void __launch_bounds__(256)
 k_cam_tris(const float4* __restrict__ prims, float4* __restrict__ cam_prims, int n, float ox, float oy, float oz) {
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
-        const float4* p = prims + 3 * (size_t)slot;
+        const float4* p = prims + kTriStride * (size_t)slot;
         float4 r0, r1, r2;
         cam_tri_record(__ldg(p), __ldg(p + 1), __ldg(p + 2), ox, oy, oz, r0, r1, r2);
         float4* o = cam_prims + 3 * (size_t)slot;

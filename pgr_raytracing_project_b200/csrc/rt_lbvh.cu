@@ -26,6 +26,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "rt_device.cuh"
 #include "rt_lbvh.h"
 
 namespace b200rt {
@@ -245,10 +246,10 @@ __global__ void k_gather(const float* __restrict__ raw, const int* __restrict__ 
         const int p = prim_index[slot];
         if (is_tri) {
             const float* v = raw + 9 * (size_t)p;
-            prims[3 * (size_t)slot + 0] = make_float4(v[0], v[1], v[2], __int_as_float(p));
-            prims[3 * (size_t)slot + 1] = make_float4(__fsub_rn(v[3], v[0]), __fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]),
+            prims[kTriStride * (size_t)slot + 0] = make_float4(v[0], v[1], v[2], __int_as_float(p));
+            prims[kTriStride * (size_t)slot + 1] = make_float4(__fsub_rn(v[3], v[0]), __fsub_rn(v[4], v[1]), __fsub_rn(v[5], v[2]),
                                                       __int_as_float(mat_id[p]));
-            prims[3 * (size_t)slot + 2] = make_float4(__fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1]), __fsub_rn(v[8], v[2]), 0.0f);
+            prims[kTriStride * (size_t)slot + 2] = make_float4(__fsub_rn(v[6], v[0]), __fsub_rn(v[7], v[1]), __fsub_rn(v[8], v[2]), 0.0f);
         } else {
             const float* s = raw + 4 * (size_t)p;
             prims[slot] = make_float4(s[0], s[1], s[2], s[3]);
@@ -339,7 +340,7 @@ cudaError_t lbvh_build(const float* d_raw, const int* d_mat_id, bool is_tri, int
         k_emit<<<g, 256, 0, stream>>>(lo, hi, vals_sorted, n, child_l, child_r, first, last, box, kept, rank, abi);
     }
     cudaError_t e = cudaMalloc(&dev, (size_t)n_nodes * sizeof(rt_bvh_node));
-    if (e == cudaSuccess) e = cudaMalloc(&prims, nn * (is_tri ? 3 : 1) * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&prims, nn * (is_tri ? kTriStride : 1) * sizeof(float4));
     if (e != cudaSuccess) { cudaFree(abi); cudaFree(dev); cudaFree(prims); cudaFree(vals_sorted); free_all(); return e; }
     k_device_nodes<<<grid_of(n_nodes, sm_count), 256, 0, stream>>>(abi, n_nodes, dev);
     k_gather<<<g, 256, 0, stream>>>(d_raw, d_mat_id, is_tri ? 1 : 0, vals_sorted, n, prims);

@@ -19,6 +19,11 @@ namespace b200rt {
 
 namespace {
 
+#ifndef B200RT_WF_SMEM_LEVELS
+#define B200RT_WF_SMEM_LEVELS 16
+#endif
+constexpr int kWfSmemLevels = B200RT_WF_SMEM_LEVELS;   // traversal-stack levels of k_wf_trace kept in shared memory (HybridStack)
+
 struct WaveArgs {
     TileMap tm;
     int task0, n_tasks_wave;      // pixel tasks [task0, task0 + n_tasks_wave) of the launch's enumeration
@@ -126,7 +131,8 @@ k_wf_packet0(const __grid_constant__ SceneView sc, const float4* __restrict__ ca
     if (STATS) flush_stats(d_stats, rays, cnt);
 }
 
-template <bool TRI, bool STATS>
+// CAM: the rays of this queue are camera rays (bounce 0 of variant 2: triangle test from the per-camera table)
+template <bool TRI, bool STATS, bool CAM>
 __global__ void __launch_bounds__(kThreads)
 k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuffers wb, int bounce, int max_depth, int refill_below,
            int leaf_vote, unsigned long long* d_stats) {
@@ -136,8 +142,10 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
     const float4* __restrict__ ray_d = wb.ray_d[bounce & 1];
     const unsigned count = wb.counters[bounce];
     unsigned int* fetch = wb.counters + (max_depth + 1) + bounce;
-    int stack_code[kStackDepth];
-    float stack_tn[kStackDepth];
+    __shared__ uint2 s_stack[kWfSmemLevels][kThreads];
+    int stack_code[kStackDepth - kWfSmemLevels];
+    float stack_tn[kStackDepth - kWfSmemLevels];
+    const HybridStack<kWfSmemLevels, kThreads> stack{&s_stack[0][threadIdx.x], stack_code, stack_tn};
     Trav tv;
     tv.cur = kDone; tv.sp = 0; tv.h.t = kTMax; tv.h.prim = -1; tv.h.slot = -1;
     Counters cnt = {0, 0, 0};
@@ -173,7 +181,7 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
             continue;                               // root misses waiting to be published / more to fetch
         }
         int min_active = pool_empty ? 1 : (__popc(act) * refill_below) >> 5;
-        trav_run<TRI, STATS>(sc, r, tv, stack_code, stack_tn, min_active < 1 ? 1 : min_active, leaf_vote, cnt, bounce == 0);
+        trav_run<TRI, STATS, CAM ? 1 : 0>(sc, r, tv, stack, min_active < 1 ? 1 : min_active, leaf_vote, cnt, CAM);
     }
     if (STATS) flush_stats(d_stats, 0, cnt);
 }
@@ -280,7 +288,7 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
     const int n_tasks = work_items(tm) * 32;
     const int cap = wb.capacity;
     const int chunk = n_tasks < cap ? n_tasks : (cap & ~31);
-    const int trace_grid = resident_grid(k_wf_trace<TRI, STATS>, cfg.sm_count);
+    const int trace_grid = resident_grid(k_wf_trace<TRI, STATS, false>, cfg.sm_count);
     cudaStream_t st = cfg.stream;
     for (int task0 = 0; task0 < n_tasks; task0 += chunk) {
         int nt = n_tasks - task0 < chunk ? n_tasks - task0 : chunk;
@@ -307,8 +315,10 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
             *n_launches += 1;
             int depth = AOV ? 1 : max_depth;
             for (int b = 0; b < depth; ++b) {
-                if (!(packet0 && b == 0))
-                    k_wf_trace<TRI, STATS><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
+                if (b == 0 && !packet0)
+                    k_wf_trace<TRI, STATS, true><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
+                else if (b > 0)
+                    k_wf_trace<TRI, STATS, false><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
                 k_wf_shade<TRI, STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(sc, wa, wb, b, d_prim, d_t,
                                                                                                       cfg.d_stats);
                 *n_launches += (packet0 && b == 0) ? 1 : 2;
