@@ -71,6 +71,18 @@ int rt_set_spheres(rt_ctx* ctx, const float* h_center_radius, const float* h_mat
  * vertices: n x 9 (v0 v1 v2); material_id: n (may be NULL = 0); materials: m x 8. */
 int rt_set_triangles(rt_ctx* ctx, const float* h_vertices, const int32_t* h_material_id, int64_t n,
                      const float* h_materials, int m);
+/* Scene EDITS without a rebuild.  The reference's host re-sends the whole scene through RayTracer::set_scene -- a deep
+ * copy and two BVH builds (old/raytracer_core copy.cpp:84-87,162-167) -- on every drag / slider event
+ * (interaction.py:906,1169, gui.py:943).  rt_update_geometry replaces the positions of the n primitives of the current
+ * scene (same kind, same count, same order; n x 4 spheres or n x 9 triangles) and REFITS the current tree on the device
+ * (same topology, every box recomputed bottom-up; ~0.1 ms for 1M triangles + the upload) instead of rebuilding it.
+ * Pixels are those of a tree rebuilt from scratch, bit for bit; after large moves a refitted tree gets slower, not
+ * wrong, so every refit measures the summed surface area of the internal boxes against the tree as built and, above
+ * option "refit_limit" percent (default 200; 0 = never), drops the tree: the next launch builds a new one with option
+ * "builder".  Read-only options "refits", "refit_rebuilds", "refit_area_pct" report what happened.
+ * rt_update_materials replaces the m material rows (no BVH work at all). */
+int rt_update_geometry(rt_ctx* ctx, const float* h_prims, int64_t n);
+int rt_update_materials(rt_ctx* ctx, const float* h_material8, int m);
 /* Scene::background_color (old/raytracer_core copy.h:226; interaction.py:297). */
 int rt_set_background(rt_ctx* ctx, const float rgb[3]);
 

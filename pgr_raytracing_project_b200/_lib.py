@@ -15,7 +15,8 @@ SYMBOLS = [
     "rt_trace_primary", "rt_trace_rays", "rt_select_object", "rt_render", "rt_render_tiles", "rt_untile",
     "rt_render_host", "rt_accumulate", "rt_tonemap_u8", "rt_set_option", "rt_get_option", "rt_get_stats",
     "rt_reset_stats", "rt_build_bvh_host", "rt_render_sum", "rt_resolve", "rt_render_tiles_frame", "rt_frame_alloc",
-    "rt_frame_free", "rt_frame_open", "rt_frame_close", "rt_resolve_planes", "rt_display_u8",
+    "rt_frame_free", "rt_frame_open", "rt_frame_close", "rt_resolve_planes", "rt_display_u8", "rt_update_geometry",
+    "rt_update_materials",
 ]
 
 
@@ -55,6 +56,8 @@ def load():
         "rt_set_spheres": (ci, [vp, fp, fp, ip, i64]),
         "rt_set_triangles": (ci, [vp, fp, ip, i64, fp, ci]),
         "rt_set_background": (ci, [vp, fp]),
+        "rt_update_geometry": (ci, [vp, fp, i64]),
+        "rt_update_materials": (ci, [vp, fp, ci]),
         "rt_build_bvh": (ci, [vp, ci]),
         "rt_get_bvh": (ci, [vp, vp, C.POINTER(i64), ip]),
         "rt_set_bvh": (ci, [vp, vp, i64, ip]),

@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rt.so")
-SOURCES = ["rt_api.cu", "rt_kernels.cu", "rt_wavefront.cu", "rt_lbvh.cu", "rt_display.cu", "rt_bvh.cpp"]
-HEADERS = ["rt_device.cuh", "rt_kernels.h", "rt_kernel_common.cuh", "rt_bvh.h", "rt_lbvh.h", "rt_display.h", os.path.join("..", "..", "include", "b200rt.h")]
+SOURCES = ["rt_api.cu", "rt_kernels.cu", "rt_wavefront.cu", "rt_lbvh.cu", "rt_refit.cu", "rt_display.cu", "rt_bvh.cpp"]
+HEADERS = ["rt_device.cuh", "rt_kernels.h", "rt_kernel_common.cuh", "rt_bvh.h", "rt_lbvh.h", "rt_refit.h", "rt_display.h", os.path.join("..", "..", "include", "b200rt.h")]
 
 
 def nvcc_path() -> str:

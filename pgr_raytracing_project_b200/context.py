@@ -117,6 +117,18 @@ class RenderContext:
         self.n_prims = v.shape[0]
         self.object_id = np.arange(self.n_prims, dtype=np.int32)
 
+    def update_geometry(self, prims):
+        """Scene edit that moves primitives but keeps their number and order: new (n, 4) spheres / (n, 9) triangles;
+        the current tree is refitted on the device instead of rebuilt (rt_update_geometry)."""
+        a = np.ascontiguousarray(prims, dtype=np.float32)
+        assert a.ndim == 2 and a.shape[0] == self.n_prims
+        self._ck(self.L.rt_update_geometry(self.h, _fp(a), a.shape[0]))
+
+    def update_materials(self, material8):
+        a = np.ascontiguousarray(material8, dtype=np.float32)
+        assert a.ndim == 2 and a.shape[1] == 8
+        self._ck(self.L.rt_update_materials(self.h, _fp(a), a.shape[0]))
+
     def set_background(self, rgb):
         a = np.ascontiguousarray(rgb, dtype=np.float32)
         self._ck(self.L.rt_set_background(self.h, _fp(a)))

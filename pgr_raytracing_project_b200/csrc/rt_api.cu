@@ -18,6 +18,7 @@
 #include "rt_kernels.h"
 #include "rt_display.h"
 #include "rt_lbvh.h"
+#include "rt_refit.h"
 
 using namespace b200rt;
 
@@ -107,6 +108,11 @@ struct rt_ctx {
     void* d_display = nullptr;               // rt_display_u8 scratch (tone-mapped copy, sorted copy, sort workspace)
     size_t display_bytes = 0;
     int32_t* d_pick = nullptr;               // rt_select_object scratch: org3 dir3 | prim | t
+    void* d_edit = nullptr;                  // rt_update_geometry scratch: raw primitives + refit workspace (grow-only)
+    size_t edit_bytes = 0;
+    double built_area = 0.0;                 // tree-quality figure (bvh_area) of the tree as BUILT; 0 = not measured yet
+    int refit_limit = 200;                   // option "refit_limit": rebuild when a refit leaves more than this % of built_area (0: never)
+    int64_t refits = 0, refit_rebuilds = 0, area_pct = 100;
 };
 
 namespace {
@@ -450,7 +456,7 @@ void rt_destroy(rt_ctx* ctx) {
         cudaDeviceSynchronize();
         free_device_scene(ctx);
         free_wave(ctx);
-        cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick); cudaFree(ctx->d_display); cudaFree(ctx->d_planes);
+        cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick); cudaFree(ctx->d_edit); cudaFree(ctx->d_display); cudaFree(ctx->d_planes);
         cudaFree(ctx->d_band_cnt); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
         if (ctx->h_band_flags) cudaFreeHost(ctx->h_band_flags);
         if (ctx->render_stream) cudaStreamDestroy(ctx->render_stream);
@@ -494,6 +500,74 @@ int rt_set_triangles(rt_ctx* ctx, const float* v, const int32_t* material_id, in
         ctx->object_id[i] = (int32_t)i;
     }
     ctx->bvh_valid = false; ctx->device_valid = false; ctx->tune_state = 0; ctx->tune_pending = -1;
+    return 0;
+}
+
+int rt_update_geometry(rt_ctx* ctx, const float* h_prims, int64_t n) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (n != ctx->n) return fail(ctx, "rt_update_geometry: primitive count differs from the uploaded scene (use rt_set_spheres / rt_set_triangles)");
+    if (n == 0) return 0;
+    if (!h_prims) return fail(ctx, "rt_update_geometry: NULL array");
+    const size_t per = ctx->is_tri ? 9 : 4;
+    ctx->prim_data.assign(h_prims, h_prims + per * (size_t)n);
+    ctx->cam_table_ok = false;
+    if (!ctx->bvh_valid || !ctx->device_valid) { ctx->bvh_valid = false; ctx->device_valid = false; return 0; }   // nothing built yet: the next launch builds
+    DeviceGuard g(ctx->device);
+    const size_t raw_bytes = per * (size_t)n * sizeof(float), raw_pad = (raw_bytes + 255) & ~(size_t)255;
+    const size_t need = raw_pad + (size_t)ctx->n_nodes * 32;
+    if (need > ctx->edit_bytes) {
+        cudaFree(ctx->d_edit); ctx->d_edit = nullptr; ctx->edit_bytes = 0;
+        CK(cudaMalloc(&ctx->d_edit, need));
+        ctx->edit_bytes = need;
+    }
+    if (!ctx->d_nodes_abi) CK(cudaMalloc(&ctx->d_nodes_abi, (size_t)ctx->n_nodes * sizeof(rt_bvh_node)));
+    CK(cudaDeviceSynchronize());                                           // renders in flight on other streams still read the old boxes
+    double* d_area = reinterpret_cast<double*>(ctx->d_stats + 6);         // spare words of the 64-byte stats block
+    if (ctx->built_area == 0.0) {                                          // first edit of this tree: how good was it as built?
+        CK(bvh_area(ctx->d_nodes, (int)ctx->n_nodes, d_area, ctx->sm_count, nullptr));
+        CK(cudaMemcpy(&ctx->built_area, d_area, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    CK(cudaMemcpy(ctx->d_edit, h_prims, raw_bytes, cudaMemcpyHostToDevice));
+    CK(bvh_refit(ctx->d_nodes, ctx->d_nodes_abi, (int)ctx->n_nodes, ctx->d_slot_prim, static_cast<const float*>(ctx->d_edit), ctx->is_tri,
+                 ctx->d_prims, (int)n, static_cast<char*>(ctx->d_edit) + raw_pad, ctx->sm_count, nullptr));
+    CK(bvh_area(ctx->d_nodes, (int)ctx->n_nodes, d_area, ctx->sm_count, nullptr));
+    ctx->launches += 5;
+    ctx->refits += 1;
+    double area = 0.0;
+    CK(cudaMemcpy(&area, d_area, sizeof(double), cudaMemcpyDeviceToHost));            // synchronises
+    ctx->area_pct = ctx->built_area > 0.0 ? (int64_t)(100.0 * area / ctx->built_area) : 100;
+    if (ctx->refit_limit > 0 && ctx->area_pct > ctx->refit_limit) {                   // the edit wrecked the tree: build a new one
+        ctx->refit_rebuilds += 1;                                                     // (lazily, with option "builder", at the next launch)
+        ctx->bvh_valid = false; ctx->device_valid = false;
+        return 0;
+    }
+    rt_bvh_node root;
+    CK(cudaMemcpy(&root, ctx->d_nodes_abi, sizeof(root), cudaMemcpyDeviceToHost));
+    ctx->root_extent = 0.0f;
+    for (int k = 0; k < 3; ++k) ctx->root_extent = std::fmax(ctx->root_extent, std::fmax(std::fabs(root.bmin[k]), std::fabs(root.bmax[k])));
+    ctx->host_bvh_stale = true;                                            // rt_get_bvh downloads the refitted boxes
+    return 0;
+}
+
+int rt_update_materials(rt_ctx* ctx, const float* h_material8, int m) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (m != ctx->m) return fail(ctx, "rt_update_materials: material count differs from the uploaded scene");
+    if (m == 0) return 0;
+    if (!h_material8) return fail(ctx, "rt_update_materials: NULL array");
+    ctx->mats.assign(h_material8, h_material8 + 8 * (size_t)m);
+    ctx->tune_state = 0; ctx->tune_pending = -1;
+    if (!ctx->device_valid || !ctx->d_mats) return 0;                        // uploaded with the scene later
+    DeviceGuard g(ctx->device);
+    std::vector<float4> mats((size_t)m * 2);
+    for (int k = 0; k < m; ++k) {
+        const float* q = &ctx->mats[8 * (size_t)k];
+        mats[2 * k + 0] = make_float4(q[0], q[1], q[2], q[3]);
+        mats[2 * k + 1] = make_float4(q[4], q[5], q[6], q[7]);
+    }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(ctx->d_mats, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -560,7 +634,7 @@ static int build_bvh_device(rt_ctx* ctx) {
         CK(cudaMalloc(&ctx->d_mats, mats.size() * sizeof(float4)));
         CK(cudaMemcpy(ctx->d_mats, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
     }
-    ctx->bvh_valid = true; ctx->device_valid = true;
+    ctx->bvh_valid = true; ctx->device_valid = true; ctx->built_area = 0.0;
     return 0;
 }
 
@@ -579,7 +653,7 @@ int rt_build_bvh(rt_ctx* ctx, int builder) {
     if (ctx->bvh_depth < 0) return fail(ctx, msg);
     if (ctx->bvh_depth > kStackDepth - 2) return fail(ctx, "rt_build_bvh: tree deeper than the traversal stack");
     note_host_tree(ctx);
-    ctx->bvh_valid = true; ctx->device_valid = false;
+    ctx->bvh_valid = true; ctx->device_valid = false; ctx->built_area = 0.0;
     return 0;
 }
 
@@ -634,7 +708,7 @@ int rt_set_bvh(rt_ctx* ctx, const rt_bvh_node* nodes, int64_t n_nodes, const int
     ctx->prim_index.assign(prim_index, prim_index + ctx->n);
     ctx->bvh_depth = depth;
     note_host_tree(ctx);
-    ctx->bvh_valid = true; ctx->device_valid = false;
+    ctx->bvh_valid = true; ctx->device_valid = false; ctx->built_area = 0.0;
     return 0;
 }
 
@@ -1105,6 +1179,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "kernel") { if (value < -1 || value > 4) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront), 3 (camera-ray packets) or 4 (wavefront with packet bounce 0)"); ctx->kernel = (int)value; }
     else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
     else if (k == "overlap") { if (value < 0 || value > 2) return fail(ctx, "overlap must be 0 (render, then copy), 1 (region flags + DMA copies) or 2 (tile push)"); ctx->overlap = (int)value; }
+    else if (k == "refit_limit") { if (value < 0 || value > 100000) return fail(ctx, "refit_limit must be 0 (never rebuild) or a percentage"); ctx->refit_limit = (int)value; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail(ctx, "builder must be 0 (reference median split, host) or 1 (LBVH, device)"); ctx->builder = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
     else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);
@@ -1130,6 +1205,10 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "n_prims") *value = ctx->n;
     else if (k == "n_nodes") *value = ctx->n_nodes;
     else if (k == "builder") *value = ctx->builder;
+    else if (k == "refit_limit") *value = ctx->refit_limit;
+    else if (k == "refits") *value = ctx->refits;
+    else if (k == "refit_rebuilds") *value = ctx->refit_rebuilds;
+    else if (k == "refit_area_pct") *value = ctx->area_pct;
     else return fail(ctx, "rt_get_option: unknown option '" + k + "'");
     return 0;
 }

@@ -285,16 +285,39 @@ class RayTracer:
         self._sample_offset = 0
         self.seed = 0x5EED
         self._pinned = {}                                    # (W, H) -> [ring of pinned host frames, next index]
+        self._uploaded = None                                # arrays of the last set_scene (edit detection)
+        self._refits = 0
+        self.refit_edits = True                              # set_scene of an unchanged object list refits instead of rebuilding
+        self.rebuild_every = 64
         self._push_camera()
 
     # -- scene / camera --------------------------------------------------------------------
     def set_scene(self, scene: Scene):
+        """RayTracer::set_scene (old/raytracer_core copy.cpp:162-167): the tracer's own copy of the scene + its BVH.
+        The host calls this on EVERY edit (interaction.py:675,778,906,929,953,994,1044,1169; gui.py:943,957,981), so an
+        edit that keeps the object list (same ids in the same order) does not rebuild: moved / resized spheres REFIT the
+        current tree on the device (rt_update_geometry), changed materials are re-uploaded (rt_update_materials), and a
+        scene that did not change at all costs nothing.  Same pixels as a rebuild (closest hits do not depend on the
+        tree); every ``rebuild_every``-th consecutive refit is a full rebuild so that tree quality cannot drift."""
         with self._lock:
             cr, m8, oid = scene._arrays()
-            self._ctx.set_spheres(cr, m8, oid)
             self._ctx.set_background(scene.background_color._tuple())
-            self._ctx.build_bvh(0)
-            self._debug.build_count += 1
+            last = self._uploaded
+            same_objects = (self.refit_edits and last is not None and len(oid) > 0 and np.array_equal(last[2], oid)
+                            and self._refits < self.rebuild_every)
+            if same_objects:
+                if not np.array_equal(last[0], cr):
+                    self._ctx.update_geometry(cr)
+                    self._refits += 1
+                    self._debug.refit_count = getattr(self._debug, "refit_count", 0) + 1
+                if not np.array_equal(last[1], m8):
+                    self._ctx.update_materials(m8)
+            else:
+                self._ctx.set_spheres(cr, m8, oid)
+                self._ctx.build_bvh(0)
+                self._refits = 0
+                self._debug.build_count += 1
+            self._uploaded = (cr, m8, oid)
 
     def get_camera(self) -> Camera:
         return self._camera._copy()                          # get_camera_copy, binding.cpp:100

@@ -1,0 +1,228 @@
+"""GPU tests of scene edits without a rebuild (rt_update_geometry / rt_update_materials):
+the refitted tree gives, bit for bit, the pixels of a tree rebuilt from scratch and of the CPU oracle on the edited
+scene; its boxes enclose the moved primitives; the drop-in RayTracer.set_scene takes the edit path."""
+from __future__ import annotations
+
+import copy
+import dataclasses
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from pgr_raytracing_project_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from pgr_raytracing_project_b200.context import RenderContext
+    c = RenderContext(0)
+    yield c
+    c.close()
+
+
+def _moved(scene, seed, share=0.3, amount=1.5):
+    """a copy of `scene` with `share` of its primitives displaced by up to `amount` (and, spheres, resized)."""
+    rng = np.random.default_rng(seed)
+    s = copy.deepcopy(scene)
+    n = s.n_prims
+    pick = rng.random(n) < share
+    d = (rng.random((n, 3)).astype(np.float32) * 2 - 1) * np.float32(amount)
+    d[~pick] = 0
+    if s.is_triangles:
+        v = s.vertices.reshape(n, 3, 3).copy()
+        v += d[:, None, :]
+        s.vertices = v.reshape(n, 9)
+    else:
+        cr = s.center_radius.copy()
+        cr[:, :3] += d
+        cr[pick, 3] *= rng.uniform(0.5, 1.5, size=int(pick.sum())).astype(np.float32)
+        s.center_radius = cr
+    return s
+
+
+def _prims(scene):
+    return scene.vertices if scene.is_triangles else scene.center_radius
+
+
+def _oracle(scene, cam, nodes=None, prim_index=None):
+    o = orc.OracleScene()
+    o.load(scene, build_bvh=nodes is None)
+    if nodes is not None:
+        o.set_bvh(nodes, prim_index)
+    o.set_camera(cam)
+    return o
+
+
+@pytest.mark.parametrize("make,W,H", [
+    (lambda: scenes.random_triangles(40_000, seed=31), 320, 200),
+    (lambda: scenes.random_spheres(20_000, seed=32), 320, 200),
+    (lambda: scenes.default_scene(), 160, 120),
+    (lambda: scenes.random_triangles(3, seed=2, extent=0.5, size=1.0, cam_z=4.0), 64, 48),     # root is a leaf
+])
+@pytest.mark.parametrize("builder", [0, 1])
+def test_refit_gives_the_pixels_of_a_rebuild(ctx, make, W, H, builder):
+    s0 = make()
+    s1 = _moved(s0, seed=5)
+    cam = s0.camera.as_array(W / H)
+    ctx.set_scene(s0, build_bvh=False)
+    ctx.build_bvh(builder)
+    ctx.set_camera_array(cam)
+    ctx.render(W, H, 1, 2, seed=3)                                   # the tree is on the device and in use
+    n_nodes = ctx.get_option("n_nodes")
+    ctx.update_geometry(_prims(s1))                                  # refit
+    assert ctx.get_option("n_nodes") == n_nodes                      # same topology
+    prim_r, t_r = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
+    img_r = ctx.render(W, H, 2, 3, seed=9).cpu().numpy()
+    nodes, prim_index = ctx.get_bvh()                                # the refitted tree, as the oracle will walk it
+    # (1) boxes enclose the moved primitives, leaf by leaf, and parents enclose children
+    P = _prims(s1)
+    if s1.is_triangles:
+        lo = P.reshape(-1, 3, 3).min(1); hi = P.reshape(-1, 3, 3).max(1)
+    else:
+        lo = P[:, :3] - P[:, 3:4]; hi = P[:, :3] + P[:, 3:4]
+    for k in range(len(nodes)):
+        if k == 1:
+            continue
+        nd = nodes[k]
+        if nd["b"] > 0:
+            ids = prim_index[nd["a"]:nd["a"] + nd["b"]]
+            assert np.all(lo[ids] >= nd["bmin"]) and np.all(hi[ids] <= nd["bmax"])
+        else:
+            for c in (nd["a"], nd["a"] + 1):
+                assert np.all(nodes[c]["bmin"] >= nd["bmin"]) and np.all(nodes[c]["bmax"] <= nd["bmax"])
+    # (2) oracle on the edited scene over the refitted tree and over its own rebuilt tree
+    o = _oracle(s1, cam, nodes, prim_index)
+    op, ot, _ = o.trace_primary(W, H, orc.MODE_NEAR_FIRST)
+    assert np.array_equal(prim_r, op) and np.array_equal(t_r, ot)
+    oimg, _ = o.render(W, H, 2, 3, seed=9)
+    assert np.array_equal(img_r, oimg)
+    o2 = _oracle(s1, cam)
+    op2, ot2, _ = o2.trace_primary(W, H, orc.MODE_NEAR_FIRST)
+    assert np.array_equal(prim_r, op2) and np.array_equal(t_r, ot2)
+    # (3) a context-side rebuild from scratch gives the same pixels
+    ctx.set_scene(s1, build_bvh=False)
+    ctx.build_bvh(builder)
+    prim_b, t_b = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
+    img_b = ctx.render(W, H, 2, 3, seed=9).cpu().numpy()
+    assert np.array_equal(prim_r, prim_b) and np.array_equal(t_r, t_b) and np.array_equal(img_r, img_b)
+
+
+def test_refit_twice_and_back_is_idempotent(ctx):
+    s0 = scenes.random_triangles(10_000, seed=41)
+    W, H = 200, 120
+    ctx.set_scene(s0)
+    ctx.set_camera_array(s0.camera.as_array(W / H))
+    img0 = ctx.render(W, H, 1, 2, seed=1).cpu().numpy()
+    nodes0, _ = ctx.get_bvh()
+    ctx.update_geometry(_prims(_moved(s0, seed=1)))
+    ctx.update_geometry(_prims(_moved(s0, seed=2, share=1.0, amount=4.0)))
+    assert not np.array_equal(ctx.render(W, H, 1, 2, seed=1).cpu().numpy(), img0)
+    ctx.update_geometry(_prims(s0))                                   # back where it was
+    img1 = ctx.render(W, H, 1, 2, seed=1).cpu().numpy()
+    nodes1, _ = ctx.get_bvh()
+    assert np.array_equal(img0, img1)
+    assert nodes0.tobytes() == nodes1.tobytes()                        # same topology + same primitives => the builder's own boxes
+
+
+def test_update_before_any_build_and_bad_arguments(ctx):
+    from pgr_raytracing_project_b200._lib import B200RTError
+    s0 = scenes.random_spheres(500, seed=7)
+    s1 = _moved(s0, seed=3)
+    W, H = 96, 64
+    ctx.set_scene(s0, build_bvh=False)
+    ctx.update_geometry(_prims(s1))                                   # nothing built yet: just replaces the host copy
+    ctx.set_camera_array(s0.camera.as_array(W / H))
+    prim, t = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
+    o = _oracle(s1, s0.camera.as_array(W / H))
+    op, ot, _ = o.trace_primary(W, H, orc.MODE_NEAR_FIRST)
+    assert np.array_equal(prim, op) and np.array_equal(t, ot)
+    with pytest.raises((B200RTError, AssertionError)):
+        ctx.update_geometry(_prims(s1)[:-1])
+    with pytest.raises(B200RTError):
+        ctx.update_materials(s1.material8[:-1])
+
+
+def test_update_materials_only(ctx):
+    s0 = scenes.default_scene()
+    W, H = 160, 120
+    cam = s0.camera.as_array(W / H)
+    ctx.set_scene(s0)
+    ctx.set_camera_array(cam)
+    ctx.render(W, H, 1, 3, seed=4)
+    s1 = copy.deepcopy(s0)
+    s1.material8 = s0.material8.copy()
+    s1.material8[:, 0:3] = s1.material8[:, 0:3][:, ::-1] * np.float32(0.9)     # new albedos
+    s1.material8[2, 3] = 0.7                                                   # one sphere turns metallic
+    ctx.update_materials(s1.material8)
+    img = ctx.render(W, H, 2, 4, seed=4).cpu().numpy()
+    oimg, _ = _oracle(s1, cam).render(W, H, 2, 4, seed=4)
+    assert np.array_equal(img, oimg)
+
+
+def test_drop_in_set_scene_refits_on_edit():
+    """interaction.py moves a sphere and calls ray_tracer.set_scene(scene) (:199, :906): same pixels as a fresh tracer,
+    no rebuild."""
+    from pgr_raytracing_project_b200 import raytracer_cpp as rc
+    sd = scenes.default_scene()
+    scene = rc.Scene()
+    scene.background_color = rc.Vector3(*sd.background)
+    for k in range(sd.n_prims):
+        m = rc.Material()
+        m.albedo = rc.Vector3(*sd.material8[k, 0:3])
+        m.metallic, m.roughness = float(sd.material8[k, 3]), float(sd.material8[k, 4])
+        m.emission = rc.Vector3(*sd.material8[k, 5:8])
+        sp = rc.Sphere()
+        sp.center = rc.Vector3(*sd.center_radius[k, :3])
+        sp.radius = float(sd.center_radius[k, 3])
+        sp.material, sp.object_id, sp.name = m, k, sd.names[k]
+        scene.add_sphere(sp)
+    rt = rc.RayTracer()
+    rt.seed = 11
+    rt.set_scene(scene)
+    builds = rt.get_debug_info().build_count
+    rt.render(96, 64, 1, 2)
+    scene.spheres[1].center = rc.Vector3(0.4, 0.3, -1.2)              # ObjectDragger.update_drag
+    scene.spheres[2].material.albedo = rc.Vector3(0.1, 0.9, 0.2)      # colour edit
+    rt.set_scene(scene)
+    assert rt.get_debug_info().build_count == builds                  # refitted, not rebuilt
+    rt._sample_offset = 0
+    a = np.array(rt.render(96, 64, 2, 3))
+    fresh = rc.RayTracer()
+    fresh.seed = 11
+    fresh.set_scene(scene)
+    b = np.array(fresh.render(96, 64, 2, 3))
+    assert np.array_equal(a, b)
+    scene.remove_sphere(scene.spheres[3].object_id)                   # object list changed: rebuild
+    rt.set_scene(scene)
+    assert rt.get_debug_info().build_count == builds + 1
+
+
+def test_refit_quality_guard_rebuilds_a_wrecked_tree(ctx):
+    """An edit that scatters the primitives leaves a refitted tree whose internal boxes have many times the surface area
+    of the tree as built: above option refit_limit (percent) the library drops the tree and builds a new one."""
+    s0 = scenes.random_triangles(20_000, seed=51)
+    W, H = 160, 100
+    cam = s0.camera.as_array(W / H)
+    ctx.set_scene(s0)
+    ctx.set_camera_array(cam)
+    ctx.render(W, H, 1, 1, seed=1)
+    before = ctx.get_option("refit_rebuilds")
+    small = _moved(s0, seed=1, share=0.02, amount=0.2)
+    ctx.update_geometry(_prims(small))
+    assert ctx.get_option("refit_rebuilds") == before and 100 <= ctx.get_option("refit_area_pct") < 200
+    wild = _moved(s0, seed=2, share=1.0, amount=8.0)
+    ctx.update_geometry(_prims(wild))
+    assert ctx.get_option("refit_rebuilds") == before + 1 and ctx.get_option("refit_area_pct") > 200
+    prim, t = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]              # builds the new tree
+    op, ot, _ = _oracle(wild, cam).trace_primary(W, H, orc.MODE_NEAR_FIRST)
+    assert np.array_equal(prim, op) and np.array_equal(t, ot)
+    ctx.set_option("refit_limit", 0)                                           # never rebuild: still the right pixels
+    ctx.update_geometry(_prims(s0))
+    ctx.update_geometry(_prims(wild))
+    assert ctx.get_option("refit_rebuilds") == before + 1
+    prim2, t2 = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
+    assert np.array_equal(prim2, op) and np.array_equal(t2, ot)
+    ctx.set_option("refit_limit", 200)
