@@ -277,10 +277,12 @@ def main():
     # N > 1 (weak scaling, N x 2.07 M rays per step): the frame gets N samples per pixel and is tile-partitioned --
     # every GPU renders all N samples of ITS 32x32 tiles (skew-dealt so that each rank gets a share of every tile row
     # and column) and its kernels store the resolved pixels straight into rank 0's frame (CUDA IPC + NVLink peer
-    # stores); a one-element NCCL all-reduce is the barrier.  Bit-identical to the 1-GPU frame with N spp.
+    # stores); the barrier is rt_frame_sync -- a counter in the shared frame's own memory (one atomic + a short spin over
+    # NVLink; BENCH_BARRIER=nccl selects a one-element all-reduce instead).  Bit-identical to the 1-GPU frame with N spp.
     # BENCH_EXCHANGE=samples|peer_samples selects the sample-range partitions instead.
     exchange_mode = os.environ.get("BENCH_EXCHANGE", "peer")
-    renderer = DistributedRenderer(ctx, rank, world, mode=exchange_mode)
+    barrier_mode = os.environ.get("BENCH_BARRIER", "flag")
+    renderer = DistributedRenderer(ctx, rank, world, mode=exchange_mode, barrier=barrier_mode)
     spp_total = SPP_PER_GPU * world
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=ctx.device)       # 512 MiB > 126 MB L2
 
@@ -320,7 +322,7 @@ def main():
     # ---- device-timed region: K steps, a CUDA-event pair around each step on the launching stream, L2 flushed
     # (512 MiB memset) between steps outside the event pairs.  At N > 1 a step is: this rank's 1 spp rendered
     # straight into its plane of rank 0's shared buffer (NVLink peer stores from the render kernel), a one-element
-    # NCCL all-reduce as the barrier, and on rank 0 the ordered plane sum + resolve kernel.
+    # barrier (rt_frame_sync), and on rank 0 the ordered plane sum + resolve kernel.
     ctx.reset_stats()
     sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -418,7 +420,8 @@ def main():
                 "partition": "single GPU" if world == 1 else {
                     "peer": "tiles: N spp per pixel, every GPU renders all samples of its skew-dealt 32x32 tiles and stores the "
                             "resolved pixels straight into rank 0's frame (CUDA IPC, NVLink peer stores from the kernel); barrier = "
-                            "one-element NCCL all-reduce; bit-identical to the 1-GPU frame; all inside the timed step",
+                            + ("rt_frame_sync (arrival counter in the shared frame's memory, one atomic + spin over NVLink)" if barrier_mode == "flag"
+                               else "one-element NCCL all-reduce") + "; bit-identical to the 1-GPU frame; all inside the timed step",
                     "peer_samples": "sample-range: 1 spp of the full frame per GPU, written by the render kernel into this rank's plane "
                                     "of rank 0's shared buffer (CUDA IPC); barrier; rank 0 sums the planes in rank order and resolves",
                     "samples": "sample-range: 1 spp of the full frame per GPU, NCCL reduce(SUM) to rank 0 + resolve, inside the timed step",

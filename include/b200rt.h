@@ -154,6 +154,12 @@ int rt_frame_alloc(rt_ctx* ctx, int width, int height, int planes, float** d_fra
 int rt_frame_free(rt_ctx* ctx, float* d_frame);
 int rt_frame_open(rt_ctx* ctx, const unsigned char handle[64], float** d_peer_frame);
 int rt_frame_close(rt_ctx* ctx, float* d_peer_frame);
+/* Barrier between the `world` processes that render into one shared frame, THROUGH that frame's memory (rt_frame_alloc
+ * reserves the sync words behind the planes): enqueued on `stream` after the render, it publishes this process's
+ * stores, counts the process in with one atomic on the owner's memory and returns (in stream order) once all `world`
+ * processes of frame number `epoch` (1, 2, 3, ... per shared frame, the same on every process) have arrived -- a few
+ * microseconds over NVLink instead of a collective launch.  width / height / planes as given to rt_frame_alloc. */
+int rt_frame_sync(rt_ctx* ctx, float* d_frame, int width, int height, int planes, int world, uint64_t epoch, void* stream);
 /* Full frame, raw radiance sums (no mean / gamma / clamp): the per-rank partial of a sample-range
  * partition; sum the partials (e.g. ncclReduce) and finish with rt_resolve. */
 int rt_render_sum(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed,

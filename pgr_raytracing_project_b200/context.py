@@ -252,6 +252,10 @@ class RenderContext:
                                           self._stream()))
         return out
 
+    def frame_sync(self, ptr: int, width: int, height: int, planes: int, world: int, epoch: int):
+        """Barrier between the processes sharing the frame at `ptr` (rt_frame_sync), enqueued on the current stream."""
+        self._ck(self.L.rt_frame_sync(self.h, C.c_void_p(ptr), width, height, planes, world, C.c_uint64(epoch), self._stream()))
+
     def frame_open(self, handle: bytes) -> int:
         p = C.c_void_p()
         self._ck(self.L.rt_frame_open(self.h, C.create_string_buffer(handle, 64), C.byref(p)))

@@ -861,7 +861,9 @@ int rt_frame_alloc(rt_ctx* ctx, int width, int height, int planes, float** d_fra
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     DeviceGuard g(ctx->device);
     float* p = nullptr;
-    CK(cudaMalloc(&p, (size_t)planes * width * height * 3 * sizeof(float)));
+    const size_t frame_bytes = ((size_t)planes * width * height * 3 * sizeof(float) + 255) & ~(size_t)255;
+    CK(cudaMalloc(&p, frame_bytes + 256));                               // + the sync words of rt_frame_sync
+    CK(cudaMemset(reinterpret_cast<char*>(p) + frame_bytes, 0, 256));
     cudaIpcMemHandle_t h;
     cudaError_t e = cudaIpcGetMemHandle(&h, p);
     if (e != cudaSuccess) { cudaFree(p); return cuda_fail(ctx, "cudaIpcGetMemHandle", e); }
@@ -895,6 +897,19 @@ int rt_frame_close(rt_ctx* ctx, float* d_peer_frame) {
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     DeviceGuard g(ctx->device);
     CK(cudaIpcCloseMemHandle(d_peer_frame));
+    return 0;
+}
+
+int rt_frame_sync(rt_ctx* ctx, float* d_frame, int width, int height, int planes, int world, uint64_t epoch, void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (int rc = check_frame(ctx, width, height)) return rc;
+    if (!d_frame || planes < 1 || planes > 64 || world < 1 || epoch == 0) return fail(ctx, "rt_frame_sync: bad arguments");
+    DeviceGuard g(ctx->device);
+    const size_t frame_bytes = ((size_t)planes * width * height * 3 * sizeof(float) + 255) & ~(size_t)255;
+    unsigned long long* words = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_frame) + frame_bytes);
+    CK(launch_frame_sync(words, (unsigned long long)world * epoch, (cudaStream_t)stream));
+    ctx->launches += 1;
     return 0;
 }
 

@@ -444,6 +444,22 @@ k_plane_accumulate(const __grid_constant__ TileMap tm, int n_tasks, int batch, i
     }
 }
 
+// rt_frame_sync: one thread per process.  Everything this process stored into the shared frame before this kernel
+// (stream order) is released system-wide, the process arrives (one atomic on the frame owner's memory, over NVLink
+// for the peers) and spins until all `world` processes of this epoch have arrived: target = world * epoch, the
+// counter only ever grows, so nothing is reset between frames.  A peer that never arrives ends the wait after ~2 s
+// with the error word set instead of hanging the GPU.
+__global__ void k_frame_sync(unsigned long long* words, unsigned long long target) {
+    __threadfence_system();
+    atomicAdd_system(words, 1ull);
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned long long*>(words) < target) {
+        __nanosleep(200);
+        if (clock64() - t0 > 4000000000ll) { atomicExch_system(words + 1, 1ull); break; }
+    }
+    __threadfence_system();
+}
+
 __global__ void k_untile(int width, int height, int tile_w, int tile_h, int tiles_x, int n_ranks, int tiles_per_rank,
                          const float* __restrict__ tiles, float* __restrict__ frame) {
     int64_t n = (int64_t)width * height;
@@ -647,6 +663,11 @@ cudaError_t launch_render(const SceneView& sc, bool is_tri, const CameraBlock& c
     if (is_tri) { if (st) LAUNCH(true, true) else LAUNCH(true, false) }
     else { if (st) LAUNCH(false, true) else LAUNCH(false, false) }
 #undef LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frame_sync(unsigned long long* words, unsigned long long target, cudaStream_t stream) {
+    k_frame_sync<<<1, 1, 0, stream>>>(words, target);
     return cudaGetLastError();
 }
 

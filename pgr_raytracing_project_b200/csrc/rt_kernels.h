@@ -119,6 +119,8 @@ cudaError_t launch_resolve_planes(const float* d_planes, int n_planes, int64_t p
                                   int spp_total, cudaStream_t stream);
 cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, int n_old, int n_batch,
                               cudaStream_t stream);
+// Barrier between the processes that share a frame (rt_frame_sync): words[0] = arrival counter, words[1] = error flag.
+cudaError_t launch_frame_sync(unsigned long long* words, unsigned long long target, cudaStream_t stream);
 cudaError_t launch_tonemap_u8(const float* d_accum, uint8_t* d_rgb8, int64_t n, float exposure, cudaStream_t stream);
 
 }  // namespace b200rt

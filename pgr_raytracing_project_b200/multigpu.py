@@ -103,9 +103,14 @@ def sample_range(spp: int, rank: int, world: int) -> Tuple[int, int]:
 class DistributedRenderer:
     """Tile- or sample-sharded rendering across the ranks of a torch.distributed group (NCCL)."""
 
-    def __init__(self, ctx, rank: int, world: int, mode: str = "tiles", tile: Tuple[int, int] = (32, 32), group=None):
-        assert mode in ("tiles", "samples", "peer", "peer_samples")
+    def __init__(self, ctx, rank: int, world: int, mode: str = "tiles", tile: Tuple[int, int] = (32, 32), group=None,
+                 barrier: str = "flag"):
+        """barrier (peer modes): "flag" = rt_frame_sync, a counter in the shared frame's own memory (one atomic + a
+        short spin over NVLink); "nccl" = a one-element all-reduce."""
+        assert mode in ("tiles", "samples", "peer", "peer_samples") and barrier in ("flag", "nccl")
         self.ctx, self.rank, self.world, self.mode, self.tile, self.group = ctx, rank, world, mode, tile, group
+        self.barrier = barrier
+        self._epoch = {}           # (W, H, slot) -> frames synchronised so far
         self._bufs = {}
         self._shared = {}          # (W, H, slot) -> (pointer, torch view or None, owner?)
 
@@ -134,6 +139,16 @@ class DistributedRenderer:
             self._shared[key] = (ptr, view)
             self._token = torch.zeros(1, device=self.ctx.device)
         return self._shared[key]
+
+    def _sync(self, width: int, height: int, slot: int):
+        if self.barrier == "nccl":
+            import torch.distributed as dist
+            dist.all_reduce(self._token, group=self.group)
+            return
+        key = (width, height, slot)
+        self._epoch[key] = self._epoch.get(key, 0) + 1
+        ptr, _ = self._shared[key]
+        self.ctx.frame_sync(ptr, width, height, self.world if self.mode == "peer_samples" else 1, self.world, self._epoch[key])
 
     def close(self):
         for (ptr, view) in self._shared.values():
@@ -187,12 +202,12 @@ class DistributedRenderer:
         if self.world == 1:
             return local
         if self.mode == "peer":
-            # the pixels are already in rank 0's frame; what remains is "every rank's kernel has finished":
-            # a one-element all-reduce, stream-ordered after the render kernel on every rank
-            dist.all_reduce(self._token, group=self.group)
+            # the pixels are already in rank 0's frame; what remains is "every rank's kernel has finished",
+            # stream-ordered after the render kernel on every rank
+            self._sync(width, height, slot)
             return local
         if self.mode == "peer_samples":
-            dist.all_reduce(self._token, group=self.group)
+            self._sync(width, height, slot)
             if self.rank != 0:
                 return None
             return ctx.resolve_planes(local, spp, out=self._buf(("frame", slot), (height, width, 3)))

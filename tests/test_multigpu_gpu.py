@@ -38,8 +38,8 @@ def _worker(rank, world, port, out_dir):
         c = scene.camera
         ctx.set_camera(c.position, c.target, c.up, c.fov)
         full = ctx.render(W, H, spp, depth, seed=5).cpu().numpy() if rank == 0 else None
-        for mode in ("tiles", "samples", "peer", "peer_samples"):
-            r = DistributedRenderer(ctx, rank, world, mode=mode)
+        for mode in ("tiles", "samples", "peer", "peer_samples", "peer+nccl", "peer_samples+nccl"):
+            r = DistributedRenderer(ctx, rank, world, mode=mode.split("+")[0], barrier="nccl" if mode.endswith("+nccl") else "flag")
             for slot in (0, 1, 0):                                  # buffer sets are reusable
                 frame = r.render(W, H, spp, depth, seed=5, slot=slot)
             torch.cuda.synchronize()
@@ -60,7 +60,7 @@ def test_all_partition_modes_match_single_gpu(tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for name in ("tris_d1", "default_d4"):
         full = np.load(tmp_path / f"{name}_full.npy")
-        for mode in ("tiles", "peer"):
+        for mode in ("tiles", "peer", "peer+nccl"):
             assert np.array_equal(np.load(tmp_path / f"{name}_{mode}.npy"), full), (name, mode)   # bit-identical
-        for mode in ("samples", "peer_samples"):
+        for mode in ("samples", "peer_samples", "peer_samples+nccl"):
             np.testing.assert_allclose(np.load(tmp_path / f"{name}_{mode}.npy"), full, atol=3e-6)  # re-associated sum
