@@ -69,13 +69,26 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def profile_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any."""
+def profile_traffic(key="dram_bytes_per_launch"):
+    """dram bytes (or warp instructions) per launch of the dominant kernel from the committed ncu summary, if any."""
     p = os.path.join(ROOT, "profiles", "latest_traffic.json")
     try:
-        return json.load(open(p)).get("dram_bytes_per_launch")
+        return json.load(open(p)).get(key)
     except Exception:  # noqa: BLE001
         return None
+
+
+def issue_view(kernel_ms, sm_count, sm_mhz):
+    """The limiter the ncu captures name for the camera-ray kernel is instruction issue, not bytes: warp instructions
+    per launch (ncu smsp__inst_executed.sum of the committed capture; the work per frame is deterministic) over the
+    live launch duration, against 4 issue slots per SM per cycle at the SM clock sampled during the run."""
+    inst = profile_traffic("warp_inst_per_launch")
+    if not inst or not sm_mhz:
+        return None
+    achieved = inst / (kernel_ms * 1e-3) / 1e9
+    peak = sm_count * 4 * sm_mhz * 1e6 / 1e9
+    return {"warp_inst_per_launch": inst, "achieved": achieved, "peak": peak, "unit": "G warp-inst/s", "frac": achieved / peak,
+            "source": "profiles/latest_traffic.json (ncu --set full of this kernel) / live kernel_ms"}
 
 
 class ClockSampler:
@@ -443,6 +456,7 @@ def main():
                 "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                 "rays_per_launch": rays_per_launch, "fetched_bytes_per_ray": fetched_bytes_per_ray,
                 "achieved_fetched": rays_per_launch * fetched_bytes_per_ray / (kernel_ms / 1e3) / 1e9,
+                "issue": issue_view(kernel_ms, ctx.get_option("sm_count"), (clocks or {}).get("sm_mhz")) if world == 1 else None,
                 "note": "algorithmic bytes (SURVEY 8(d)): every 32-B node record and 48-B triangle that ONE RAY's own "
                         "near-first walk fetches, no credit for cache hits or for sharing; the working set (64 MB) is "
                         "L2-resident and the packet kernel fetches each record once per 32-ray packet "
