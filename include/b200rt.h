@@ -158,7 +158,9 @@ int rt_frame_close(rt_ctx* ctx, float* d_peer_frame);
  * reserves the sync words behind the planes): enqueued on `stream` after the render, it publishes this process's
  * stores, counts the process in with one atomic on the owner's memory and returns (in stream order) once all `world`
  * processes of frame number `epoch` (1, 2, 3, ... per shared frame, the same on every process) have arrived -- a few
- * microseconds over NVLink instead of a collective launch.  width / height / planes as given to rt_frame_alloc. */
+ * microseconds over NVLink instead of a collective launch.  A process that has not arrived after about 20 s is taken
+ * for lost: the waiting kernels trap, so every waiting process fails at its next CUDA call rather than reading an
+ * incomplete frame.  width / height / planes as given to rt_frame_alloc. */
 int rt_frame_sync(rt_ctx* ctx, float* d_frame, int width, int height, int planes, int world, uint64_t epoch, void* stream);
 /* Full frame, raw radiance sums (no mean / gamma / clamp): the per-rank partial of a sample-range
  * partition; sum the partials (e.g. ncclReduce) and finish with rt_resolve. */

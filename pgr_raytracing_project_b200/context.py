@@ -152,10 +152,9 @@ class RenderContext:
 
     # ------------------------------------------------------------------ camera
     def set_camera(self, position, target, up=(0.0, 1.0, 0.0), fov: float = 45.0, aspect: float = 0.0):
-        p = np.asarray(position, dtype=np.float64)
-        t = np.asarray(target, dtype=np.float64)
-        u = np.asarray(up, dtype=np.float64)
-        self._ck(self.L.rt_set_camera(self.h, _dp(p), _dp(t), _dp(u), float(fov), float(aspect)))
+        d3 = C.c_double * 3                                   # plain ctypes arrays: this call sits on the per-frame path
+        self._ck(self.L.rt_set_camera(self.h, d3(*[float(x) for x in position]), d3(*[float(x) for x in target]),
+                                      d3(*[float(x) for x in up]), float(fov), float(aspect)))
 
     def set_camera_array(self, cam11):
         c = np.asarray(cam11, dtype=np.float64)
@@ -281,8 +280,8 @@ class RenderContext:
         if out is None:
             out = np.empty((height, width, 3), dtype=np.float32)
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == height * width * 3
-        self._ck(self.L.rt_render_host(self.h, width, height, spp, max_depth, C.c_uint64(seed),
-                                       C.c_uint32(sample_offset), out.ctypes.data_as(C.c_void_p)))
+        self._ck(self.L.rt_render_host(self.h, width, height, spp, max_depth, seed, sample_offset,
+                                       out.__array_interface__["data"][0]))
         return out
 
     # ------------------------------------------------------------------ framebuffer plumbing

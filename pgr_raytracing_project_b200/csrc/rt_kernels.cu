@@ -447,15 +447,16 @@ k_plane_accumulate(const __grid_constant__ TileMap tm, int n_tasks, int batch, i
 // rt_frame_sync: one thread per process.  Everything this process stored into the shared frame before this kernel
 // (stream order) is released system-wide, the process arrives (one atomic on the frame owner's memory, over NVLink
 // for the peers) and spins until all `world` processes of this epoch have arrived: target = world * epoch, the
-// counter only ever grows, so nothing is reset between frames.  A peer that never arrives ends the wait after ~2 s
-// with the error word set instead of hanging the GPU.
+// counter only ever grows, so nothing is reset between frames.  A peer that has not arrived after ~20 s is a lost
+// process: the error word is set and the kernel traps, so that this process fails loudly at its next CUDA call
+// instead of hanging the GPU or handing out an incomplete frame.
 __global__ void k_frame_sync(unsigned long long* words, unsigned long long target) {
     __threadfence_system();
     atomicAdd_system(words, 1ull);
     const long long t0 = clock64();
     while (*reinterpret_cast<volatile unsigned long long*>(words) < target) {
         __nanosleep(200);
-        if (clock64() - t0 > 4000000000ll) { atomicExch_system(words + 1, 1ull); break; }
+        if (clock64() - t0 > 40000000000ll) { atomicExch_system(words + 1, 1ull); __trap(); }
     }
     __threadfence_system();
 }

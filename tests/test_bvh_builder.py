@@ -52,3 +52,14 @@ def test_million_triangle_build_time():
     dt = time.time() - t0
     assert len(index) == 1_000_000 and len(nodes) > 500_000
     assert dt < 30.0, f"host build of 1M triangles took {dt:.1f}s"
+
+
+def test_refit_restatement_reproduces_the_builders_boxes():
+    """tests/refit_ref.py (the checker the GPU refit tests compare against, bit for bit) applied to an UNMOVED scene must
+    give back exactly the boxes the reference-order builder wrote: same leaf boxes, same unions, same padding."""
+    from refit_ref import refit_numpy
+    for s in (scenes.random_triangles(5000, seed=3), scenes.random_spheres(3000, seed=4), scenes.default_scene(),
+              scenes.random_triangles(3, seed=2, extent=0.5, size=1.0, cam_z=4.0)):
+        P = s.vertices if s.is_triangles else s.center_radius
+        nodes, prim_index = build_bvh_host(P, s.is_triangles)
+        assert refit_numpy(nodes, prim_index, P, s.is_triangles).tobytes() == nodes.tobytes()

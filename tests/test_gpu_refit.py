@@ -11,6 +11,7 @@ import pytest
 
 from oracle import oracle as orc
 from pgr_raytracing_project_b200 import scenes
+from refit_ref import refit_numpy as _refit_numpy
 
 pytestmark = pytest.mark.gpu
 
@@ -93,6 +94,8 @@ def test_refit_gives_the_pixels_of_a_rebuild(ctx, make, W, H, builder):
         else:
             for c in (nd["a"], nd["a"] + 1):
                 assert np.all(nodes[c]["bmin"] >= nd["bmin"]) and np.all(nodes[c]["bmax"] <= nd["bmax"])
+    want = _refit_numpy(nodes, prim_index, P, s1.is_triangles)
+    assert nodes.tobytes() == want.tobytes()                           # every box, bit for bit, vs the CPU restatement
     # (2) oracle on the edited scene over the refitted tree and over its own rebuilt tree
     o = _oracle(s1, cam, nodes, prim_index)
     op, ot, _ = o.trace_primary(W, H, orc.MODE_NEAR_FIRST)
