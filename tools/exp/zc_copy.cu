@@ -22,6 +22,44 @@ __global__ void k_tiles(const float4* __restrict__ src, float4* __restrict__ dst
         }
     }
 }
+// d) bulk (TMA) stores: each CTA stages CHUNK bytes in shared memory with ordinary loads, then ONE thread issues
+//    cp.async.bulk.global.shared::cta for the whole chunk (UBLKCP): does the async-proxy path packetise better on PCIe?
+template <int CHUNK>
+__global__ void k_bulk(const float4* __restrict__ src, float4* __restrict__ dst, size_t n4) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4* buf = reinterpret_cast<float4*>(smem);
+    const size_t per = CHUNK / 16, n_chunks = n4 / per;
+    for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        for (int k = threadIdx.x; k < (int)per; k += blockDim.x) buf[k] = src[c * per + k];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned s_addr = (unsigned)__cvta_generic_to_shared(buf);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst + c * per), "r"(s_addr), "r"(CHUNK) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncthreads();
+    }
+}
+// e) the same with 384-byte rows at a frame pitch (the tile pattern): 32 bulk stores per tile
+__global__ void k_bulk_tiles(const float4* __restrict__ src, float4* __restrict__ dst, int tiles_x, int tiles_y, int pitch4) {
+    __shared__ __align__(128) float4 buf[32 * 24];
+    for (int t = blockIdx.x; t < tiles_x * tiles_y; t += gridDim.x) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        const size_t base = (size_t)ty * 32 * pitch4 + (size_t)tx * 24;
+        for (int k = threadIdx.x; k < 32 * 24; k += blockDim.x) buf[k] = src[base + (size_t)(k / 24) * pitch4 + (k % 24)];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned s_addr = (unsigned)__cvta_generic_to_shared(buf + threadIdx.x * 24);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 384;" :: "l"(dst + base + (size_t)threadIdx.x * pitch4), "r"(s_addr) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncthreads();
+    }
+}
 int main() {
     const int W = 1920, H = 1080;
     const size_t bytes = (size_t)W * H * 12, n4 = bytes / 16;
@@ -47,6 +85,18 @@ int main() {
         for (int rep = 0; rep < 3; ++rep) {
             cudaEventRecord(a); k_tiles<<<g, 256>>>(d, hd, W / 32, (H + 31) / 32 - 1, W * 12 / 16); cudaEventRecord(b); CK(cudaEventSynchronize(b));
             cudaEventElapsedTime(&ms, a, b); if (rep == 2) report("tile copy (33 of 34 rows), CTAs", g, ms);
+        }
+    }
+    for (int g : {8, 37, 148, 296}) {
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(a); k_bulk<16384><<<g, 256, 16384>>>(d, hd, n4); cudaEventRecord(b); CK(cudaEventSynchronize(b));
+            cudaEventElapsedTime(&ms, a, b); if (rep == 2) report("bulk store 16 KB chunks, CTAs", g, ms);
+        }
+    }
+    for (int g : {8, 37, 148, 296}) {
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(a); k_bulk_tiles<<<g, 256>>>(d, hd, W / 32, (H + 31) / 32 - 1, W * 12 / 16); cudaEventRecord(b); CK(cudaEventSynchronize(b));
+            cudaEventElapsedTime(&ms, a, b); if (rep == 2) report("bulk store tiles (33/34 rows), CTAs", g, ms);
         }
     }
     return 0;
