@@ -87,6 +87,23 @@ int main() {
             cudaEventElapsedTime(&ms, a, b); if (rep == 2) report("tile copy (33 of 34 rows), CTAs", g, ms);
         }
     }
+    {   // f) DMA engine and SM stores AT THE SAME TIME, each moving a share of the frame: does the link take more than either alone?
+        cudaStream_t s1, s2; cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking); cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+        cudaEvent_t e1, e2; cudaEventCreate(&e1); cudaEventCreate(&e2);
+        for (int pct : {30, 50, 70}) {
+            const size_t n_dma = (n4 * pct / 100) & ~(size_t)63;
+            for (int rep = 0; rep < 3; ++rep) {
+                cudaDeviceSynchronize();
+                cudaEventRecord(a, s1);
+                cudaStreamWaitEvent(s2, a, 0);
+                CK(cudaMemcpyAsync(h, d, n_dma * 16, cudaMemcpyDeviceToHost, s1));
+                k_flat<<<37, 256, 0, s2>>>(d + n_dma, hd + n_dma, n4 - n_dma);
+                cudaEventRecord(e2, s2); cudaStreamWaitEvent(s1, e2, 0);
+                cudaEventRecord(b, s1); CK(cudaEventSynchronize(b));
+                cudaEventElapsedTime(&ms, a, b); if (rep == 2) report("DMA (pct of bytes) + SM stores", pct, ms);
+            }
+        }
+    }
     for (int g : {8, 37, 148, 296}) {
         for (int rep = 0; rep < 3; ++rep) {
             cudaEventRecord(a); k_bulk<16384><<<g, 256, 16384>>>(d, hd, n4); cudaEventRecord(b); CK(cudaEventSynchronize(b));
