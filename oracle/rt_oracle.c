@@ -322,9 +322,15 @@ int64_t orc_get_bvh(const scene_t* s, void* nodes, int32_t* prim_index) {
 typedef struct { v3 o, d, inv, ood; } ray_t;
 typedef struct { float t; int32_t prim; uint64_t n_node, n_prim; } hit_t;
 
+/* 1/d of the slab test.  A direction component that is zero (an axis-parallel ray) or too small for 1/d to stay finite
+ * gets +-2^80 instead: a power of two, so o * inv and the slab distances fmaf(plane, inv, -o * inv) = (plane - o) * 2^80
+ * are exact, finite and sign-correct -- the ray is inside the slab iff lo <= o <= hi, as in the reference's
+ * (plane - o) * (1/d) form (old/bvh copy.cpp:9-25) -- where inf would make o * inv - o * inv a NaN and lose the box. */
+static inline float safe_inv(float d) { return fabsf(d) < 0x1p-80f ? copysignf(0x1p80f, d) : 1.0f / d; }
+
 static inline ray_t make_ray(v3 o, v3 dir_unit) {     /* raytracer_core.h:113-115 */
     ray_t r; r.o = o; r.d = dir_unit;
-    r.inv.x = 1.0f / dir_unit.x; r.inv.y = 1.0f / dir_unit.y; r.inv.z = 1.0f / dir_unit.z;
+    r.inv.x = safe_inv(dir_unit.x); r.inv.y = safe_inv(dir_unit.y); r.inv.z = safe_inv(dir_unit.z);
     r.ood.x = o.x * r.inv.x; r.ood.y = o.y * r.inv.y; r.ood.z = o.z * r.inv.z;
     return r;
 }

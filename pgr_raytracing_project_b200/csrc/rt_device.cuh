@@ -92,10 +92,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ float u01(uint32_t x) { return __fmul_rn((float)(x >> 8), 0x1p-24f); }
 
 // ------------------------------------------------------------------------------- rays
+// 1/d of the slab test.  A direction component that is zero (an axis-parallel ray) or too small for 1/d to stay finite
+// gets +-2^80 instead: a power of two, so o * inv and the slab distances fmaf(plane, inv, -o * inv) = (plane - o) * 2^80 are
+// exact, finite and sign-correct -- the ray is inside the slab iff lo <= o <= hi, as in the reference's (plane - o) * (1/d)
+// form (old/bvh copy.cpp:9-25) -- where inf would make o * inv - o * inv a NaN and lose the box.  (oracle: safe_inv)
+__device__ __forceinline__ float safe_inv(float d) { return fabsf(d) < 0x1p-80f ? copysignf(0x1p80f, d) : __fdiv_rn(1.0f, d); }
+
 __device__ __forceinline__ Ray make_ray(float ox, float oy, float oz, float dx, float dy, float dz) {
     Ray r;
     r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
-    r.ix = __fdiv_rn(1.0f, dx); r.iy = __fdiv_rn(1.0f, dy); r.iz = __fdiv_rn(1.0f, dz);
+    r.ix = safe_inv(dx); r.iy = safe_inv(dy); r.iz = safe_inv(dz);
     r.ax = __fmul_rn(ox, r.ix); r.ay = __fmul_rn(oy, r.iy); r.az = __fmul_rn(oz, r.iz);
     return r;
 }

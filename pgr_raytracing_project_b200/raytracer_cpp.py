@@ -286,6 +286,7 @@ class RayTracer:
         self.seed = 0x5EED
         self._pinned = {}                                    # (W, H) -> [ring of pinned host frames, next index]
         self._uploaded = None                                # arrays of the last set_scene (edit detection)
+        self._background = np.array([0.1, 0.1, 0.1])         # Scene::Scene()
         self._refits = 0
         self.refit_edits = True                              # set_scene of an unchanged object list refits instead of rebuilding
         self.rebuild_every = 64
@@ -302,6 +303,7 @@ class RayTracer:
         with self._lock:
             cr, m8, oid = scene._arrays()
             self._ctx.set_background(scene.background_color._tuple())
+            self._background = np.array(scene.background_color._tuple(), dtype=np.float64)
             last = self._uploaded
             same_objects = (self.refit_edits and last is not None and len(oid) > 0 and np.array_equal(last[2], oid)
                             and self._refits < self.rebuild_every)
@@ -377,8 +379,49 @@ class RayTracer:
             return self._ctx.select_object(x, y, width, height)
 
     def trace_ray(self, ray: Ray, depth: int, max_depth: int) -> Vector3:
-        raise NotImplementedError("RayTracer.trace_ray: single-ray radiance queries are not part of the "
-                                  "accelerated path (unused by the reference host)")
+        """RayTracer::trace_ray (old/raytracer_core copy.cpp:211-243; binding.cpp:104), unrolled from its recursion:
+        radiance along one ray, `depth` segments at most.  A debugging query the host never calls: every closest hit is
+        one 1-ray rt_trace_rays launch on the device, the shading between two hits is v1's, in double precision, with
+        Python's generator standing in for v1's random_device-seeded mt19937 (so, as in the reference, two calls differ)."""
+        import random
+        with self._lock:
+            if self._uploaded is None or depth <= 0:
+                return Vector3(0.0, 0.0, 0.0)
+            cr, m8, _ = self._uploaded
+            bg = self._background
+            color, thr = np.zeros(3), np.ones(3)
+            o = np.array(ray.origin._tuple(), dtype=np.float64)
+            d = np.array(ray.direction._tuple(), dtype=np.float64)
+
+            def unit_sphere():
+                while True:
+                    p = np.array([random.random(), random.random(), random.random()]) * 2.0 - 1.0
+                    if p @ p < 1.0:
+                        return p
+
+            for remaining in range(depth, 0, -1):
+                prim, t = self._ctx.trace_rays(o[None].astype(np.float32), d[None].astype(np.float32))
+                k, t = int(prim[0]), float(t[0])
+                if k < 0:
+                    color += thr * bg
+                    break
+                dn = d / np.linalg.norm(d)
+                p = o + dn * t
+                n = (p - cr[k, :3].astype(np.float64)) / float(cr[k, 3])
+                if dn @ n > 0.0:                                         # HitRecord::set_face_normal
+                    n = -n
+                albedo, metallic, roughness, emission = m8[k, 0:3], float(m8[k, 3]), float(m8[k, 4]), m8[k, 5:8]
+                color += thr * emission
+                if not (remaining < 3 or random.random() < 0.8):        # v1's unweighted Russian roulette
+                    break
+                if random.random() < metallic:
+                    d = (dn - n * (2.0 * (dn @ n))) + unit_sphere() * roughness
+                else:
+                    h = unit_sphere()
+                    d = n + (h if h @ n > 0.0 else -h)
+                thr = thr * albedo
+                o = p
+            return Vector3(*[float(x) for x in color])
 
     def set_debug_mode(self, enable: bool):
         self._debug.enable_debug = bool(enable)

@@ -165,10 +165,7 @@ def test_update_materials_only(ctx):
     assert np.array_equal(img, oimg)
 
 
-def test_drop_in_set_scene_refits_on_edit():
-    """interaction.py moves a sphere and calls ray_tracer.set_scene(scene) (:199, :906): same pixels as a fresh tracer,
-    no rebuild."""
-    from pgr_raytracing_project_b200 import raytracer_cpp as rc
+def _default_scene_objects(rc):
     sd = scenes.default_scene()
     scene = rc.Scene()
     scene.background_color = rc.Vector3(*sd.background)
@@ -182,6 +179,46 @@ def test_drop_in_set_scene_refits_on_edit():
         sp.radius = float(sd.center_radius[k, 3])
         sp.material, sp.object_id, sp.name = m, k, sd.names[k]
         scene.add_sphere(sp)
+    return scene
+
+
+def test_drop_in_trace_ray():
+    """RayTracer.trace_ray (binding.cpp:104; old/raytracer_core copy.cpp:211-243): the deterministic cases of v1's
+    recursion, and the expectation of the random ones against the renderer itself."""
+    from pgr_raytracing_project_b200 import raytracer_cpp as rc
+    scene = _default_scene_objects(rc)
+    rt = rc.RayTracer()
+    rt.set_scene(scene)
+    up = rc.Ray(rc.Vector3(0, 5, 5), rc.Vector3(0, 1, 0))
+    assert rt.trace_ray(up, 0, 4)._tuple() == (0.0, 0.0, 0.0)                       # depth <= 0
+    assert rt.trace_ray(up, 4, 4)._tuple() == pytest.approx((0.05, 0.05, 0.1))      # miss: background
+    light = rc.Ray(rc.Vector3(0, 3, 5), rc.Vector3(0, 0, -1))                        # straight at "Main Light"
+    assert rt.trace_ray(light, 1, 4)._tuple() == pytest.approx((10.0, 10.0, 8.0))   # emitted + 0 * albedo
+    # expectation: a ray onto the ground, 2 segments = emitted(0) + albedo * E[radiance of the bounce ray's hit or miss];
+    # the renderer's depth-2 radiance of the same camera ray is the same expectation (linear: undo the sqrt gamma).
+    # Without the three emitters the only light is the background, so both estimates have little variance.
+    for oid in (6, 7, 8):
+        scene.remove_sphere(oid)
+    rt.set_scene(scene)
+    cam = rt.get_camera()
+    cam.position, cam.target, cam.fov = rc.Vector3(0, 2, 5), rc.Vector3(0, 0, -1), 45.0
+    rt.set_camera(cam)
+    W, H = 64, 48
+    img = np.array(rt.render(W, H, 4096, 2), dtype=np.float64).reshape(H, W, 3)
+    j, i = 40, 20                                                                    # a ground pixel away from the spheres
+    want = img[j, i] ** 2
+    c = rt.get_camera()
+    c.aspect_ratio = W / H
+    r = c.get_ray((i + 0.5) / W, (j + 0.5) / H)
+    got = np.mean([rt.trace_ray(r, 2, 2)._tuple() for _ in range(3000)], axis=0)
+    assert 0.0 < want.min() and want.max() < 1.0 and np.allclose(got, want, rtol=0.1, atol=0.002), (got, want)
+
+
+def test_drop_in_set_scene_refits_on_edit():
+    """interaction.py moves a sphere and calls ray_tracer.set_scene(scene) (:199, :906): same pixels as a fresh tracer,
+    no rebuild."""
+    from pgr_raytracing_project_b200 import raytracer_cpp as rc
+    scene = _default_scene_objects(rc)
     rt = rc.RayTracer()
     rt.seed = 11
     rt.set_scene(scene)
@@ -229,3 +266,25 @@ def test_refit_quality_guard_rebuilds_a_wrecked_tree(ctx):
     prim2, t2 = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
     assert np.array_equal(prim2, op) and np.array_equal(t2, ot)
     ctx.set_option("refit_limit", 200)
+
+
+def test_axis_parallel_rays_and_centre_click(ctx):
+    """Rays with a zero / denormal direction component (safe_inv): the device walk agrees with the oracle's brute force,
+    and a click exactly at the centre of a symmetric view (an axis-parallel ray) picks the object in front."""
+    s = scenes.default_scene()
+    ctx.set_scene(s)
+    org = np.array([[0, 3, 5], [0, 5, -1], [-5, 0.5, -3], [0, 3, 5], [2, 0.5, 5], [0, 2, 5], [0, 0.3, 7]], dtype=np.float32)
+    d = np.array([[0, 0, -1], [0, -1, 0], [1, 0, 0], [0, 0, 1], [0, 0, -1], [0, -1e-42, -1], [0, 0, -1]], dtype=np.float32)
+    prim, t = [x.cpu().numpy() for x in ctx.trace_rays(org, d)]
+    pb, tb, _ = orc.OracleScene(s).trace_rays(org, d, orc.MODE_BRUTE)
+    assert np.array_equal(prim, pb) and np.array_equal(t, tb) and prim.tolist() == [6, 6, 1, -1, 3, -1, 2]
+    ctx.set_camera((0.0, 0.5, 5.0), (0.0, 0.5, -3.0), (0, 1, 0), 45.0)       # looks straight down -z at the green sphere
+    assert ctx.select_object(0.5, 0.5, 640, 480) == 2
+    tri = scenes.random_triangles(20_000, seed=5)
+    ctx.set_scene(tri)
+    o3 = np.zeros((64, 3), dtype=np.float32); o3[:, 2] = 30.0
+    o3[:, 0] = np.linspace(-8, 8, 64, dtype=np.float32)
+    d3 = np.tile(np.array([[0, 0, -1]], dtype=np.float32), (64, 1))
+    prim, t = [x.cpu().numpy() for x in ctx.trace_rays(o3, d3)]
+    pb, tb, _ = orc.OracleScene(tri).trace_rays(o3, d3, orc.MODE_BRUTE)
+    assert np.array_equal(prim, pb) and np.array_equal(t, tb) and (prim >= 0).sum() > 10
