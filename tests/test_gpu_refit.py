@@ -288,3 +288,16 @@ def test_axis_parallel_rays_and_centre_click(ctx):
     prim, t = [x.cpu().numpy() for x in ctx.trace_rays(o3, d3)]
     pb, tb, _ = orc.OracleScene(tri).trace_rays(o3, d3, orc.MODE_BRUTE)
     assert np.array_equal(prim, pb) and np.array_equal(t, tb) and (prim >= 0).sum() > 10
+
+
+@pytest.mark.parametrize("trial", range(8))
+def test_adversarial_rays_device_equals_brute_force(ctx, trial):
+    """The same adversarial cases on the device (host-built and device-built tree) against the oracle's brute force."""
+    from adversarial import make_case
+    s, org, d = make_case(trial)
+    p0, t0, _ = orc.OracleScene(s).trace_rays(org, d, orc.MODE_BRUTE)
+    for builder in (0, 1):
+        ctx.set_scene(s, build_bvh=False)
+        ctx.build_bvh(builder)
+        prim, t = [x.cpu().numpy() for x in ctx.trace_rays(org, d)]
+        assert np.array_equal(prim, p0) and np.array_equal(t, t0), builder
