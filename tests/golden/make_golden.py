@@ -17,6 +17,7 @@ CUDA path, to the reference:
   spheres1000_primary.npz  1000 random spheres, 200x150: ids + distances (BVH path)
   spheres1000_rays.npz     4096 incoherent rays through Scene::hit on the same scene
   camera_rays.npz          Camera::get_ray for three cameras on a 9x9 (u,v) grid
+  camera_rays_degenerate.npz  the same for views straight down / up (right-vector fallback) and the axis-aligned C3 camera
   select_object.npz        RayTracer::select_object on a 16x12 click grid (default scene)
   default9_v1_images.npz   RayTracer::render at 160x120: 4096 spp depth 4, 2048 spp depth 2,
                            2048 spp depth 1 (v1's RNG is random_device-seeded mt19937, so these are
@@ -89,6 +90,18 @@ def main():
             for b, u in enumerate(uv):
                 rays[k, a, b] = ref_v1.camera_get_ray(c, u, v)[1]
     np.savez_compressed(os.path.join(HERE, "camera_rays.npz"), cams=np.array(cams), uv=uv, dirs=rays)
+
+    # degenerate views: straight down / straight up (forward x world-up = 0: right falls back to (1,0,0),
+    # old/raytracer_core copy.h:170-172) and the axis-aligned C3 camera
+    cams2 = [ref_v1.cam_array((0.0, 5.0, 0.0), (0.0, 0.0, 0.0), fov=45.0, aspect=4 / 3),
+             ref_v1.cam_array((1.0, -3.0, 2.0), (1.0, 4.0, 2.0), fov=70.0, aspect=1.0),
+             ref_v1.cam_array((0.0, 0.0, 30.0), (0.0, 0.0, 0.0), fov=45.0, aspect=16 / 9)]
+    rays2 = np.zeros((len(cams2), 9, 9, 3))
+    for k, c in enumerate(cams2):
+        for a, v in enumerate(uv):
+            for b, u in enumerate(uv):
+                rays2[k, a, b] = ref_v1.camera_get_ray(c, u, v)[1]
+    np.savez_compressed(os.path.join(HERE, "camera_rays_degenerate.npz"), cams=np.array(cams2), uv=uv, dirs=rays2)
 
     clicks = np.array([[(i + 0.5) / 16, (j + 0.5) / 12] for j in range(12) for i in range(16)])
     sel = np.array([rs.select_object(cam, x, y, W, H) for x, y in clicks], dtype=np.int32)

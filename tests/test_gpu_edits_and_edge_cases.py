@@ -1,9 +1,11 @@
 """GPU tests of scene edits without a rebuild (rt_update_geometry / rt_update_materials):
 the refitted tree gives, bit for bit, the pixels of a tree rebuilt from scratch and of the CPU oracle on the edited
-scene; its boxes enclose the moved primitives; the drop-in RayTracer.set_scene takes the edit path."""
+scene; its boxes enclose the moved primitives; the drop-in RayTracer.set_scene takes the edit path.  Plus the edge
+cases: RayTracer.trace_ray, axis-parallel rays, adversarial (grid-snapped) scenes and rays, degenerate cameras."""
 from __future__ import annotations
 
 import copy
+import os
 import dataclasses
 
 import numpy as np
@@ -301,3 +303,30 @@ def test_adversarial_rays_device_equals_brute_force(ctx, trial):
         ctx.build_bvh(builder)
         prim, t = [x.cpu().numpy() for x in ctx.trace_rays(org, d)]
         assert np.array_equal(prim, p0) and np.array_equal(t, t0), builder
+
+
+def test_degenerate_cameras(ctx, golden_dir):
+    """Views straight down / up (right-vector fallback) and the axis-aligned C3 camera: the library's camera block is the
+    oracle's, its rays are the v1 reference's (golden), and the primary AOV through such a camera is bit-exact."""
+    g = np.load(os.path.join(golden_dir, "camera_rays_degenerate.npz"))
+    s = scenes.default_scene()
+    ctx.set_scene(s)
+    o = orc.OracleScene(s)
+    W, H = 96, 72
+    for k, cam in enumerate(g["cams"]):
+        cam = cam.copy()
+        ctx.set_camera_array(cam)
+        o.set_camera(cam)
+        cb = ctx.camera_block()
+        assert np.array_equal(cb, o.camera_block())
+        fwd, right, up, sx, sy = cb[3:6], cb[6:9], cb[9:12], cb[12], cb[13]
+        for a, v in enumerate(g["uv"]):
+            for b, u in enumerate(g["uv"]):
+                d = fwd + right * ((u - 0.5) * 2 * sx) + up * ((0.5 - v) * 2 * sy)
+                np.testing.assert_allclose(d / np.linalg.norm(d), g["dirs"][k, a, b], rtol=0, atol=1e-12)
+        cam[10] = W / H
+        ctx.set_camera_array(cam)
+        o.set_camera(cam)
+        prim, t = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
+        op, ot, _ = o.trace_primary(W, H, orc.MODE_BRUTE)
+        assert np.array_equal(prim, op) and np.array_equal(t, ot)
