@@ -334,9 +334,9 @@ def main():
     torch.cuda.synchronize()
 
     # ---- device-timed region: K steps, a CUDA-event pair around each step on the launching stream, L2 flushed
-    # (512 MiB memset) between steps outside the event pairs.  At N > 1 a step is: this rank's 1 spp rendered
-    # straight into its plane of rank 0's shared buffer (NVLink peer stores from the render kernel), a one-element
-    # barrier (rt_frame_sync), and on rank 0 the ordered plane sum + resolve kernel.
+    # (512 MiB memset) between steps outside the event pairs.  At N > 1 a step is: this rank's tiles of the N-spp frame
+    # rendered and stored straight into rank 0's frame (NVLink peer stores from the render kernels), then the barrier
+    # (rt_frame_sync) -- see the partition description in `config`.
     ctx.reset_stats()
     sampler = ClockSampler(local_rank)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
