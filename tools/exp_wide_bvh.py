@@ -28,9 +28,18 @@ def wide_children(k, width):
         ch.remove(c); ch += [int(A[c]), int(A[c]) + 1]
     return ch
 
-def box_t(k, o, inv):
-    t1 = (bmin[k] - o) * inv; t2 = (bmax[k] - o) * inv
+def box_t(k, o, inv, lo=None, hi=None):
+    lo = bmin[k] if lo is None else lo; hi = bmax[k] if hi is None else hi
+    t1 = (lo - o) * inv; t2 = (hi - o) * inv
     return max(np.minimum(t1, t2).max(), 1e-3), np.maximum(t1, t2).min()
+
+QBITS = int(os.environ.get("QBITS", "0"))      # > 0: child boxes quantised conservatively to that many bits against the wide node's own box
+
+def quantised(parent, c):
+    plo, phi = bmin[parent], bmax[parent]
+    cell = (phi - plo) / (2 ** QBITS - 1)
+    cell = np.where(cell > 0, cell, 1.0)
+    return plo + np.floor((bmin[c] - plo) / cell) * cell, plo + np.ceil((bmax[c] - plo) / cell) * cell
 
 def tri_t(p, o, d):
     v0, e1, e2 = V[p, 0], V[p, 1] - V[p, 0], V[p, 2] - V[p, 0]
@@ -62,7 +71,7 @@ def walk(o, d, width, cache):
         hits = []
         for c in ch:
             boxes += 1
-            n, f = box_t(c, o, inv)
+            n, f = box_t(c, o, inv, *quantised(k, c)) if QBITS else box_t(c, o, inv)
             if n <= min(f, best): hits.append((n, c))
         hits.sort(reverse=True)                       # nearest on top of the stack
         stack += hits
@@ -73,4 +82,5 @@ o = rng.uniform(-9, 9, (N_RAYS, 3)); d = rng.normal(size=(N_RAYS, 3)); d /= np.l
 for width, name, node_bytes in ((2, "binary (today): 64-B pair, 2 x LDG.256", 64), (4, "BVH4 collapse", None), (8, "BVH8 collapse", None)):
     cache = {}
     r = np.array([walk(o[k], d[k], width, cache) for k in range(N_RAYS)], dtype=np.float64).mean(0)
+    if QBITS: name += " (%d-bit child boxes)" % QBITS
     print("%-42s steps/ray %6.1f  boxes/ray %6.1f  triangles/ray %5.1f" % (name, *r), flush=True)
