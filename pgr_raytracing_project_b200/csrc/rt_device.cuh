@@ -246,7 +246,7 @@ __device__ __forceinline__ void test_prim(const SceneView& sc, int slot, const R
 // code, code + 1; a pair is 64-byte aligned); code <= -2: leaf, ~code = (first_slot << 3) | count.
 constexpr int kDone = -1;
 
-// Closest hit over the flattened BVH: sibling pairs fetched as 4 x LDG.128 (ld.global.nc.v4),
+// Closest hit over the flattened BVH: sibling pairs fetched as 2 x LDG.256 (ldg_pair: ld.global.nc.v8.f32),
 // nearer child first, farther child pushed with its entry distance, dropped on pop when that
 // distance exceeds the closest hit.  (Same visiting order as oracle MODE_NEAR_FIRST, so the
 // node / primitive counters agree exactly with the CPU checker.)

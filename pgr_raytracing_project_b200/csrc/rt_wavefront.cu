@@ -5,7 +5,8 @@
 //   per bounce b:
 //     k_wf_trace      persistent threads; every lane pulls the next ray of queue b as soon as its own
 //                     traversal is finished (one atomic per refill, lanes ranked by ballot/popc), so the
-//                     warps stay full while the walk per ray is exactly intersect()'s -> hit records
+//                     warps stay full while the walk per ray is exactly intersect()'s -> hit records; the first
+//                     kWfSmemLevels levels of every lane's traversal stack live in shared memory (HybridStack)
 //     k_wf_shade      one thread per ray of queue b: emission / background, Russian roulette, scatter;
 //                     surviving paths are appended to queue b+1 (ballot/popc compaction)
 //   k_wf_accumulate   per pixel: add the wave's samples IN SAMPLE ORDER to the running sum (so the
