@@ -17,6 +17,7 @@ CUDA path, to the reference:
   spheres1000_primary.npz  1000 random spheres, 200x150: ids + distances (BVH path)
   spheres1000_rays.npz     4096 incoherent rays through Scene::hit on the same scene
   camera_rays.npz          Camera::get_ray for three cameras on a 9x9 (u,v) grid
+  spheres1000_v1_images.npz   v1 RayTracer::render of the 1000-sphere scene with metallic / emissive materials (BVH + every integrator branch)
   camera_rays_degenerate.npz  the same for views straight down / up (right-vector fallback) and the axis-aligned C3 camera
   select_object.npz        RayTracer::select_object on a 16x12 click grid (default scene)
   default9_v1_images.npz   RayTracer::render at 160x120: 4096 spp depth 4, 2048 spp depth 2,
@@ -116,6 +117,23 @@ def main():
                         depth4_4096spp=img4.astype(np.float32), depth2_2048spp=img2.astype(np.float32),
                         depth1_2048spp=img1.astype(np.float32))
     print("images: means", img4.mean((0, 1)), img2.mean((0, 1)), img1.mean((0, 1)))
+
+    # a BVH scene for the integrator: the 1000 spheres with a third of them metallic (varied roughness) and 3 % emitters
+    rng = np.random.default_rng(1007)
+    m8 = s2.material8.copy()
+    met = rng.random(1000) < 0.33
+    m8[met, 3] = rng.uniform(0.3, 1.0, met.sum())
+    m8[met, 4] = rng.uniform(0.0, 0.6, met.sum())
+    em = rng.random(1000) < 0.03
+    m8[em, 5:8] = rng.uniform(2.0, 8.0, (em.sum(), 3))
+    Ws, Hs = 128, 96
+    cams = s2.camera.as_array(Ws / Hs)
+    r3 = ref_v1.RefScene(s2.center_radius, m8, s2.object_id, s2.background)
+    s4, _ = r3.render(cams, Ws, Hs, 4096, 4)
+    s2i, _ = r3.render(cams, Ws, Hs, 2048, 2)
+    np.savez_compressed(os.path.join(HERE, "spheres1000_v1_images.npz"), width=Ws, height=Hs, cam=cams, seed=7,
+                        material8=m8.astype(np.float32), depth4_4096spp=s4.astype(np.float32),
+                        depth2_2048spp=s2i.astype(np.float32))
 
 
 if __name__ == "__main__":

@@ -330,3 +330,19 @@ def test_degenerate_cameras(ctx, golden_dir):
         prim, t = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
         op, ot, _ = o.trace_primary(W, H, orc.MODE_BRUTE)
         assert np.array_equal(prim, op) and np.array_equal(t, ot)
+
+
+def test_bvh_scene_image_vs_v1_reference(ctx, golden_dir):
+    """The device integrator over a BVH scene with metallic / emissive materials against the v1 reference's converged
+    image (tests/golden/spheres1000_v1_images.npz): PSNR >= 30 dB at 1024 spp, channel means within 1 %."""
+    g = np.load(os.path.join(golden_dir, "spheres1000_v1_images.npz"))
+    W, H = int(g["width"]), int(g["height"])
+    s = scenes.random_spheres(1000, seed=int(g["seed"]), extent=4.0, rmin=0.05, rmax=0.3, cam_z=12.0)
+    s.material8 = g["material8"].astype(np.float32)
+    ctx.set_scene(s)
+    ctx.set_camera_array(g["cam"])
+    for key, depth in (("depth4_4096spp", 4), ("depth2_2048spp", 2)):
+        img = ctx.render(W, H, 1024, depth, seed=0x5EED0007).cpu().numpy().astype(np.float64)
+        rmse = float(np.sqrt(np.mean((img - g[key]) ** 2)))
+        assert 20 * np.log10(1.0 / rmse) >= 30.0, (key, rmse)
+        np.testing.assert_allclose(img.mean((0, 1)), g[key].mean((0, 1)), rtol=0.01)
