@@ -18,6 +18,7 @@ CUDA path, to the reference:
   spheres1000_rays.npz     4096 incoherent rays through Scene::hit on the same scene
   camera_rays.npz          Camera::get_ray for three cameras on a 9x9 (u,v) grid
   spheres1000_v1_images.npz   v1 RayTracer::render of the 1000-sphere scene with metallic / emissive materials (BVH + every integrator branch)
+  spheres_mixed_rays.npz      Scene::hit on 8192 rays over 300 spheres of radius 0.01 .. 1000, origins inside spheres / grazing
   camera_rays_degenerate.npz  the same for views straight down / up (right-vector fallback) and the axis-aligned C3 camera
   select_object.npz        RayTracer::select_object on a 16x12 click grid (default scene)
   default9_v1_images.npz   RayTracer::render at 160x120: 4096 spp depth 4, 2048 spp depth 2,
@@ -117,6 +118,32 @@ def main():
                         depth4_4096spp=img4.astype(np.float32), depth2_2048spp=img2.astype(np.float32),
                         depth1_2048spp=img1.astype(np.float32))
     print("images: means", img4.mean((0, 1)), img2.mean((0, 1)), img1.mean((0, 1)))
+
+    # closest hits over five decades of radius (0.01 .. 8 and a radius-1000 ground), a third of the ray origins INSIDE a
+    # sphere (far root, flipped normal), a third grazing the ground: the 1e-5 distance bar where it is hardest
+    rng = np.random.default_rng(2026)
+    nm = 300
+    cm = rng.uniform(-20, 20, (nm, 3))
+    rm = np.exp(rng.uniform(np.log(0.01), np.log(8.0), nm))
+    cm[0] = [0, -1000.5, 0]
+    rm[0] = 1000.0
+    crm = np.concatenate([cm, rm[:, None]], 1).astype(np.float32)
+    mr = 8192
+    orgm = rng.uniform(-25, 25, (mr, 3)).astype(np.float32)
+    orgm[:, 1] = np.abs(orgm[:, 1])
+    km = rng.integers(1, nm, mr // 3)
+    um = rng.normal(size=(mr // 3, 3))
+    um /= np.linalg.norm(um, axis=1, keepdims=True)
+    orgm[:mr // 3] = (crm[km, :3] + um * crm[km, 3:4] * rng.uniform(0, 0.95, (mr // 3, 1))).astype(np.float32)
+    orgm[mr // 3:2 * (mr // 3), 1] = rng.uniform(-0.49, 0.5, mr // 3).astype(np.float32)
+    tgtm = rng.uniform(-25, 25, (mr, 3)).astype(np.float32)
+    dm = (tgtm - orgm).astype(np.float32)
+    dm[mr // 3:2 * (mr // 3), 1] *= 0.02
+    m8m = np.tile(np.array([0.7, 0.7, 0.7, 0, 0.5, 0, 0, 0], np.float32), (nm, 1))
+    rmx = ref_v1.RefScene(crm, m8m, np.arange(nm, dtype=np.int32), (0.05, 0.05, 0.1))
+    idm, tm = rmx.hit_rays(orgm.astype(np.float64), dm.astype(np.float64))
+    np.savez_compressed(os.path.join(HERE, "spheres_mixed_rays.npz"), center_radius=crm, org=orgm, dir=dm,
+                        ids=idm.astype(np.int16), t=tm)
 
     # a BVH scene for the integrator: the 1000 spheres with a third of them metallic (varied roughness) and 3 % emitters
     rng = np.random.default_rng(1007)
