@@ -346,3 +346,20 @@ def test_bvh_scene_image_vs_v1_reference(ctx, golden_dir):
         rmse = float(np.sqrt(np.mean((img - g[key]) ** 2)))
         assert 20 * np.log10(1.0 / rmse) >= 30.0, (key, rmse)
         np.testing.assert_allclose(img.mean((0, 1)), g[key].mean((0, 1)), rtol=0.01)
+
+
+def test_mixed_radius_rays_device(ctx, golden_dir):
+    """tests/golden/spheres_mixed_rays.npz on the device: spheres of radius 0.01 ... 1000, ray origins inside spheres and
+    grazing the ground -- the oracle's hits bit for bit, the v1 reference's ids, its distances within 1e-5 relative."""
+    g = np.load(os.path.join(golden_dir, "spheres_mixed_rays.npz"))
+    s = scenes.random_spheres(len(g["center_radius"]), seed=1)
+    s.center_radius = g["center_radius"].astype(np.float32)
+    s.object_id = np.arange(len(s.center_radius), dtype=np.int32)
+    ctx.set_scene(s)
+    prim, t = [x.cpu().numpy() for x in ctx.trace_rays(g["org"], g["dir"])]
+    op, ot, _ = orc.OracleScene(s).trace_rays(g["org"], g["dir"], orc.MODE_BRUTE)
+    assert np.array_equal(prim, op) and np.array_equal(t, ot)
+    ref = g["ids"].astype(np.int32)
+    assert (prim == ref).mean() >= 0.9995
+    m = (prim == ref) & (prim >= 0)
+    assert (np.abs(t[m] - g["t"][m]) / g["t"][m]).max() <= 1e-5
