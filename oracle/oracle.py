@@ -54,6 +54,7 @@ def lib():
     L.orc_render.argtypes = [vp] + [C.c_int] * 8 + [C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int, fp, u64p]
     L.orc_philox.argtypes = [u32p, u32p, u32p]
     L.orc_num_threads.restype = C.c_int
+    L.orc_set_num_threads.argtypes = [C.c_int]
     _lib = L
     return L
 
@@ -73,6 +74,11 @@ def philox(ctr, key):
     p = C.POINTER(C.c_uint32)
     lib().orc_philox(c.ctypes.data_as(p), k.ctypes.data_as(p), o.ctypes.data_as(p))
     return o
+
+
+def set_num_threads(n: int):
+    """OpenMP threads of every later oracle call (overrides the launcher's OMP_NUM_THREADS)."""
+    lib().orc_set_num_threads(int(n))
 
 
 class OracleScene:

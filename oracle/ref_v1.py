@@ -35,6 +35,7 @@ def _load(flavour: str):
     ip = C.POINTER(C.c_int32)
     vp = C.c_void_p
     lib.ref_num_threads.restype = C.c_int
+    lib.ref_set_num_threads.argtypes = [C.c_int]
     lib.ref_scene_new.restype = vp
     lib.ref_scene_free.argtypes = [vp]
     lib.ref_scene_add_spheres.argtypes = [vp, dp, dp, ip, C.c_int64]
@@ -56,6 +57,10 @@ def _load(flavour: str):
     lib.ref_tracer_render.restype = C.c_double
     _libs[flavour] = lib
     return lib
+
+
+def set_num_threads(n: int, flavour: str = "fast"):
+    _load(flavour).ref_set_num_threads(int(n))
 
 
 def _dp(a):

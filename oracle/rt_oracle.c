@@ -657,3 +657,13 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* bench.py's reference arm: a launcher (torch.distributed.run) exports OMP_NUM_THREADS=1 to its
+ * workers; the CPU arm is to use every host core whatever the launcher says. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

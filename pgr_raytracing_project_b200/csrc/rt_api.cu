@@ -110,6 +110,12 @@ struct rt_ctx {
     int32_t* d_pick = nullptr;               // rt_select_object scratch: org3 dir3 | prim | t
     void* d_edit = nullptr;                  // rt_update_geometry scratch: raw primitives + refit workspace (grow-only)
     size_t edit_bytes = 0;
+    // Context-owned scratch (work counter, wave buffers, sample planes, chunk schedule, camera table, stats) is shared by
+    // every launch.  Launches on ONE stream are ordered by the stream; a launch on a DIFFERENT stream than the previous one
+    // first waits for that one's completion event (ScratchOrder), so two streams can never advance each other's counters.
+    cudaEvent_t scratch_ev = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_pending = false;
     double built_area = 0.0;                 // tree-quality figure (bvh_area) of the tree as BUILT; 0 = not measured yet
     int refit_limit = 200;                   // option "refit_limit": rebuild when a refit leaves more than this % of built_area (0: never)
     int64_t refits = 0, refit_rebuilds = 0, area_pct = 100;
@@ -169,6 +175,19 @@ CameraBlock camera_block(const rt_ctx* c, double aspect) {
 }
 
 int ensure_bvh(rt_ctx* ctx);
+
+// RAII around every group of launches that uses context-owned scratch on `stream`: on entry, if the previous such group
+// ran on another stream, make `stream` wait for it; on exit, record the completion event the next group may have to wait on.
+struct ScratchOrder {
+    rt_ctx* c; cudaStream_t st;
+    ScratchOrder(rt_ctx* ctx, void* stream) : c(ctx), st((cudaStream_t)stream) {
+        if (!c->scratch_ev) cudaEventCreateWithFlags(&c->scratch_ev, cudaEventDisableTiming);
+        if (c->scratch_pending && c->scratch_stream != st) cudaStreamWaitEvent(st, c->scratch_ev, 0);
+    }
+    ~ScratchOrder() {
+        if (c->scratch_ev && cudaEventRecord(c->scratch_ev, st) == cudaSuccess) { c->scratch_stream = st; c->scratch_pending = true; }
+    }
+};
 
 void free_wave(rt_ctx* c) {
     for (int k = 0; k < 2; ++k) { cudaFree(c->wave.ray_o[k]); cudaFree(c->wave.ray_d[k]); c->wave.ray_o[k] = c->wave.ray_d[k] = nullptr; }
@@ -269,6 +288,7 @@ SceneView scene_view(const rt_ctx* c) {
 // wavefront queues, with the coherent bounce 0 walked by packets; single-segment (camera-ray) work favours
 // the packet kernel.
 int pick_kernel(const rt_ctx* c, int max_depth) {
+    if (max_depth == 0) return 1;                                  // RayTracer::trace_ray(depth <= 0): no segment, black frame -- one kernel for it
     if (c->kernel >= 0) {
         if (c->kernel == 3 && max_depth != 1) return 0;        // packets handle camera rays only
         if (c->kernel == 4 && max_depth == 1) return 3;
@@ -462,6 +482,7 @@ void rt_destroy(rt_ctx* ctx) {
         if (ctx->render_stream) cudaStreamDestroy(ctx->render_stream);
         if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
         if (ctx->tune_ev0) { cudaEventDestroy(ctx->tune_ev0); cudaEventDestroy(ctx->tune_ev1); }
+        if (ctx->scratch_ev) cudaEventDestroy(ctx->scratch_ev);
     }
     delete ctx;
 }
@@ -742,8 +763,9 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
     ctx->aspect = (double)width / height;            // RayTracer::render, old/raytracer_core copy.cpp:259
     CameraBlock cam = camera_block(ctx, ctx->aspect);
     TileMap tm = full_frame_map(width, height);
+    if (is_wavefront(pick_kernel(ctx, 1))) { if (int rc = ensure_wave(ctx, task_count(tm), 1, 1)) return rc; }
+    ScratchOrder order(ctx, stream);
     if (is_wavefront(pick_kernel(ctx, 1))) {
-        if (int rc = ensure_wave(ctx, task_count(tm), 1, 1)) return rc;
         int nl = 0;
         LaunchCfg wcfg = launch_cfg(ctx, stream);
         claim_cam_table(ctx, wcfg, cam);
@@ -766,6 +788,7 @@ int rt_trace_rays(rt_ctx* ctx, const float* d_origin, const float* d_direction, 
     if (n < 0 || (n > 0 && (!d_origin || !d_direction || !d_prim || !d_t))) return fail(ctx, "rt_trace_rays: bad arguments");
     DeviceGuard g(ctx->device);
     if (int rc = ensure_device(ctx)) return rc;
+    ScratchOrder order(ctx, stream);
     CK(launch_trace_rays(scene_view(ctx), ctx->is_tri, d_origin, d_direction, n, d_prim, d_t, launch_cfg(ctx, stream)));
     if (n) ctx->launches += 1;
     return 0;
@@ -817,8 +840,9 @@ static int render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile
     tm.first_tile = first_tile; tm.tile_stride = tile_stride;
     tm.n_local_tiles = first_tile < tm.n_tiles ? (tm.n_tiles - first_tile + tile_stride - 1) / tile_stride : 0;
     tm.compact = layout == 0 ? 1 : 0; tm.skew = layout == 0 ? 0 : 1;
+    if (is_wavefront(pick_kernel(ctx, max_depth)) && tm.n_local_tiles) { if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc; }
+    ScratchOrder order(ctx, stream);
     if (is_wavefront(pick_kernel(ctx, max_depth)) && tm.n_local_tiles) {
-        if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
         int nl = 0;
         LaunchCfg wcfg = launch_cfg(ctx, stream, max_depth);
         claim_cam_table(ctx, wcfg, cam);
@@ -924,10 +948,10 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
     CameraBlock cam = camera_block(ctx, ctx->aspect);
     TileMap tm = full_frame_map(width, height);
     const bool tuned = tunes(ctx, max_depth);
-    if (tuned) { if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc; }   // allocate outside the timed events
+    if (tuned || is_wavefront(pick_kernel(ctx, max_depth))) { if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc; }   // allocate outside the timed events
+    ScratchOrder order(ctx, stream);
     const int variant = tuned ? tune_begin(ctx, (cudaStream_t)stream, (double)width * height * spp) : pick_kernel(ctx, max_depth);
     if (is_wavefront(variant)) {
-        if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc;
         int nl = 0;
         LaunchCfg wcfg = launch_cfg(ctx, stream, max_depth, variant);
         claim_cam_table(ctx, wcfg, cam);
@@ -1011,6 +1035,7 @@ static int render_host_overlapped(rt_ctx* ctx, int width, int height, int spp, u
     ctx->aspect = (double)width / height;
     CameraBlock cam = camera_block(ctx, ctx->aspect);
     TileMap tm = full_frame_map(width, height);
+    ScratchOrder order(ctx, ctx->render_stream);
     LaunchCfg cfg = launch_cfg(ctx, ctx->render_stream, 1);
     BandSignal& bs = cfg.band;
     bs.cnt = ctx->d_band_cnt;
@@ -1078,6 +1103,7 @@ static int render_host_push(rt_ctx* ctx, int width, int height, int spp, uint64_
         CK(cudaMalloc(&ctx->d_tile_cnt, (size_t)tm.n_tiles * sizeof(unsigned int)));
         ctx->tile_cnt_cap = tm.n_tiles;
     }
+    ScratchOrder order(ctx, ctx->render_stream);
     LaunchCfg cfg = launch_cfg(ctx, ctx->render_stream, 1);
     BandSignal& bs = cfg.band;
     bs.cnt = ctx->d_tile_cnt; bs.flags = nullptr; bs.host_fb = d_host;
@@ -1180,6 +1206,7 @@ int rt_display_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n,
         ctx->display_bytes = need;
     }
     int nl = 0;
+    ScratchOrder order(ctx, stream);
     CK(launch_display_u8(d_accum, d_rgb8, n, exposure, ctx->d_display, ctx->display_bytes, (cudaStream_t)stream, &nl));
     ctx->launches += nl;
     return 0;

@@ -523,3 +523,89 @@ def test_c3_million_triangles_full_frame(ctx):
     st = ctx.stats()
     ctx.set_option("stats", 0)
     _check_counters(ctx, st, int(ost[1]), int(ost[2]))
+    # the RENDER instance at full size -- what bench.py times: one jittered sample per pixel, max_depth 1, resolved
+    # (for the packet variants this is k_packet<TRI,0,0,0>, not the AOV instance above) -- device frame and the
+    # host-buffer call (tile push into a page-locked frame), both bit-exact against the oracle's frame
+    seed = 0x5EED0003
+    img = ctx.render(W, H, 1, 1, seed=seed, sample_offset=5).cpu().numpy()
+    oimg, _ = o.render(W, H, 1, 1, seed=seed, sample_offset=5)
+    assert np.array_equal(img, oimg)
+    pinned = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+    ctx.render_host(W, H, 1, 1, seed=seed, sample_offset=5, out=pinned.numpy())
+    assert np.array_equal(pinned.numpy(), oimg)
+    # two samples per pixel (item mode of the packet kernel: (block, sample) work items + ordered plane sum)
+    img2 = ctx.render(W, H, 2, 1, seed=seed, sample_offset=5).cpu().numpy()
+    assert np.array_equal(img2, o.render(W, H, 2, 1, seed=seed, sample_offset=5)[0])
+
+
+def test_c4_ten_million_triangles():
+    """BASELINE config 4 at full size: 10M random triangles (seed 20260004, extent 21.5, camera z 64.5), 3840x2160.
+    Tree built ON THE DEVICE (LBVH) -- the host median split of 10M triangles is not what a user would wait for -- and
+    handed to the oracle (rt_get_bvh), which walks the same tree: the whole 8.3-megapixel primary frame (ids and
+    distances bit-exact), one million incoherent rays (origins inside the cloud, random directions), and a band of the
+    16-spp-style multi-bounce render (2 spp, max_depth 4) bit-exact; plus properties on the full 4K multi-bounce frame.
+    This is the one configuration whose working set (~1.1 GB) does not fit L2."""
+    import torch
+    from pgr_raytracing_project_b200.context import RenderContext
+    n = 10_000_000
+    s = scenes.random_triangles(n, seed=20260004, extent=21.5, cam_z=64.5)
+    W, H = 3840, 2160
+    ctx = RenderContext(0)
+    try:
+        ctx.set_scene(s, build_bvh=False)
+        ctx.build_bvh(1)
+        cam = s.camera.as_array(W / H)
+        ctx.set_camera_array(cam)
+        prim, t = ctx.trace_primary(W, H)
+        prim, t = prim.cpu().numpy(), t.cpu().numpy()
+        o = _oracle_for(ctx, s, cam)
+        op, ot, _ = o.trace_primary(W, H, orc.MODE_NEAR_FIRST)
+        assert np.array_equal(prim, op) and np.array_equal(t, ot)
+        assert 0.3 < (prim >= 0).mean() < 0.98 and prim.max() < n
+        rng = np.random.default_rng(44)
+        m = 1_000_000
+        org = rng.uniform(-20.0, 20.0, size=(m, 3)).astype(np.float32)
+        d = rng.normal(size=(m, 3)).astype(np.float32)
+        gp, gt = ctx.trace_rays(org, d)                      # both sides normalise the directions themselves
+        gp, gt = gp.cpu().numpy(), gt.cpu().numpy()
+        rp, rt_, _ = o.trace_rays(org, d)
+        assert np.array_equal(gp, rp) and np.array_equal(gt, rt_)
+        assert (gp >= 0).mean() > 0.5
+        # multi-bounce render: a 3840x64 band against the oracle, the full frame through properties
+        img = ctx.render(W, H, 2, 4, seed=0x5EED0004).cpu().numpy()
+        y0 = H // 2 - 32
+        band, _ = o.render(W, H, 2, 4, seed=0x5EED0004, rect=(0, y0, W, 64))
+        assert np.array_equal(img[y0:y0 + 64], band)
+        assert np.isfinite(img).all() and img.min() >= 0.0 and img.max() <= 1.0
+        again = ctx.render(W, H, 2, 4, seed=0x5EED0004).cpu().numpy()
+        assert np.array_equal(img, again)
+    finally:
+        ctx.close()
+
+
+def test_sphere_twin_vs_v1_reference():
+    """The 1M-sphere twin of C3 -- the only form of the headline workload the REAL reference can render: primary hit
+    ids of the device against the unmodified v1 reference (oracle/_ref strict build, Scene::hit over ITS OWN pointer
+    BVH) on a 480x270 frame: identical ids, distances within 1e-5 relative."""
+    from oracle import ref_v1
+    if not ref_v1.available("strict"):
+        pytest.skip("oracle/_ref not built (no /root/reference at build time)")
+    from pgr_raytracing_project_b200.context import RenderContext
+    s = scenes.random_spheres(1_000_000, seed=20260003)
+    W, H = 480, 270
+    cam = s.camera.as_array(W / H)
+    ctx = RenderContext(0)
+    try:
+        ctx.set_scene(s)
+        ctx.set_camera_array(cam)
+        prim, t = ctx.trace_primary(W, H)
+        ids = ctx.to_object_id(prim.cpu().numpy())
+        t = t.cpu().numpy()
+    finally:
+        ctx.close()
+    rs = ref_v1.RefScene(s.center_radius, s.material8, s.object_id, s.background, flavour="strict")
+    rid, rt_, _, _ = rs.primary(cam, W, H)
+    assert np.array_equal(ids, rid)
+    hit = rid >= 0
+    assert hit.mean() > 0.3
+    assert np.max(np.abs(t[hit] - rt_[hit]) / rt_[hit]) <= REL_T

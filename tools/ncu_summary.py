@@ -10,7 +10,11 @@ KEYS = ['gpu__time_duration.sum', 'smsp__thread_inst_executed_per_inst_executed.
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__inst_executed.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
-        'lts__t_bytes.sum', 'l1tex__t_bytes.sum', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'lts__t_bytes.sum', 'l1tex__t_bytes.sum', 'l1tex__t_sectors.sum', 'lts__t_sectors.sum',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'smsp__inst_executed_op_shared_ld.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
@@ -40,6 +44,24 @@ def main():
         for k in KEYS:
             if k in hdr:
                 print('   %-82s %s %s' % (k, r[hdr.index(k)], units[hdr.index(k)]))
+
+        def num(k):
+            try:
+                return float(r[hdr.index(k)].replace(',', '')), units[hdr.index(k)]
+            except (ValueError, IndexError):
+                return None, None
+        dur, du = num('gpu__time_duration.sum')
+        if dur:
+            sec = dur * {'ns': 1e-9, 'us': 1e-6, 'ms': 1e-3, 's': 1.0}.get(du, 1e-9)
+            scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+            for k, label in (('l1tex__t_bytes.sum', 'achieved L1TEX GB/s'), ('lts__t_bytes.sum', 'achieved L2 GB/s')):
+                v, u = num(k)
+                if v is not None:
+                    print('   %-82s %.1f' % (label + ' (= %s / duration)' % k, v * scale.get(u, 1.0) / sec / 1e9))
+            rd, ru = num('dram__bytes_read.sum')
+            wr, wu = num('dram__bytes_write.sum')
+            if rd is not None and wr is not None:
+                print('   %-82s %.1f' % ('achieved HBM GB/s (= dram read + write / duration)', (rd * scale.get(ru, 1.0) + wr * scale.get(wu, 1.0)) / sec / 1e9))
     if not bucket:
         return
     rows = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv", "--print-source", "sass"]))))
