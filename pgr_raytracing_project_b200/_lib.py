@@ -33,7 +33,9 @@ _lib = None
 
 
 def load():
-    """Load libb200rt.so (building it first if the sources are newer and nvcc is present)."""
+    """Load libb200rt.so; when the file is MISSING and nvcc is present it is built first.  A library older than its
+    sources is loaded as it is (file times do not survive the copy to the GPU box, so staleness cannot be judged there):
+    run `python -m pgr_raytracing_project_b200.build` -- or __graft_entry__.build() -- after editing csrc/."""
     global _lib
     if _lib is not None:
         return _lib

@@ -33,28 +33,60 @@ def flags() -> list:
         "-O3", "-std=c++17", "-lineinfo", "-fmad=false", *os.environ.get("B200RT_NVCC_EXTRA", "").split(),
         "-Xcompiler", "-fPIC,-fopenmp,-O2,-fno-fast-math,-ffp-contract=off",
         "-Xptxas", "-v",
-        "-shared",
     ]
+
+
+def _deps() -> list:
+    return [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
 
 
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Every translation unit to an object file (in parallel; an object is reused while it is newer than its source,
+    every header and this script), then one link.  The objects live in build/ (git-ignored)."""
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + flags() + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB, "-lgomp"]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    hdr_t = max(hdr_t, os.path.getmtime(os.path.abspath(__file__)))
+    extra = os.environ.get("B200RT_NVCC_EXTRA", "")
+    stamp = os.path.join(objdir, "flags.txt")
+    if not os.path.exists(stamp) or open(stamp).read() != extra:
+        force = True
+        with open(stamp, "w") as f:
+            f.write(extra)
+
+    def compile_one(src):
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_t):
+            return obj, "", 0
+        cmd = [nvcc_path()] + flags() + ["-c", path, "-o", obj]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, " ".join(cmd) + "\n" + proc.stdout + proc.stderr, proc.returncode
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    log = "".join(r[1] for r in results)
+    bad = [r for r in results if r[2] != 0]
+    if not bad:
+        cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"] + [r[0] for r in results] + ["-o", LIB, "-lgomp"]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+        if proc.returncode != 0:
+            bad = [(LIB, log, proc.returncode)]
     with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-4000:])
+        f.write(log)
+    if bad:
+        raise RuntimeError("nvcc failed:\n" + log[-6000:])
     if verbose:
         print(log)
     return LIB

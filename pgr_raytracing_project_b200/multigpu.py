@@ -113,6 +113,8 @@ class DistributedRenderer:
         self._epoch = {}           # (W, H, slot) -> frames synchronised so far
         self._bufs = {}
         self._shared = {}          # (W, H, slot) -> (pointer, torch view or None, owner?)
+        self._next_slot = {}       # (W, H) -> slot of the next frame when the caller does not name one (0 / 1 alternating)
+        self._token = None         # one-element tensor of the NCCL barrier
 
     def _buf(self, key, shape):
         import torch
@@ -137,12 +139,15 @@ class DistributedRenderer:
             if self.rank != 0:
                 ptr = self.ctx.frame_open(bytes(h.cpu().numpy().tobytes()))
             self._shared[key] = (ptr, view)
-            self._token = torch.zeros(1, device=self.ctx.device)
+            self._epoch[key] = 0       # a new frame's sync words start at zero
         return self._shared[key]
 
     def _sync(self, width: int, height: int, slot: int):
         if self.barrier == "nccl":
+            import torch
             import torch.distributed as dist
+            if self._token is None:
+                self._token = torch.zeros(1, device=self.ctx.device)
             dist.all_reduce(self._token, group=self.group)
             return
         key = (width, height, slot)
@@ -151,12 +156,30 @@ class DistributedRenderer:
         self.ctx.frame_sync(ptr, width, height, self.world if self.mode == "peer_samples" else 1, self.world, self._epoch[key])
 
     def close(self):
+        """Releases the shared frames (collective in effect: every rank closes).  The renderer can be used again
+        afterwards: frames, their sync words and the frame counters all start afresh."""
+        import torch
+        torch.cuda.synchronize(self.ctx.device)
         for (ptr, view) in self._shared.values():
             (self.ctx.frame_free if self.rank == 0 else self.ctx.frame_close)(ptr)
         self._shared = {}
+        self._epoch = {}
+        self._next_slot = {}
 
-    def render(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0, slot: int = 0):
-        """tiles: the resolved frame on every rank.  samples: the resolved frame on rank 0 (None elsewhere)."""
+    def render(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0, slot=None):
+        """tiles: the resolved frame on every rank.  samples / peer modes: the resolved frame on rank 0 (None elsewhere).
+
+        Peer modes -- lifetime of the returned frame.  It is a view of LIVE shared memory that the other ranks' kernels
+        store into.  There is one barrier per frame, after the stores, so a rank that has passed the barrier of frame k
+        may already be writing frame k + 1.  Frames therefore alternate between two shared buffers (`slot` None = the
+        renderer alternates 0 / 1 itself): frame k + 1 goes to the other buffer, and nobody can touch frame k's buffer again
+        before rank 0 has ARRIVED at the barrier of frame k + 1 -- which, in stream order, is after everything rank 0
+        enqueued on this stream to consume frame k (a copy, a resolve, an accumulate).  So: the returned frame stays
+        valid until the render call AFTER the next one, provided it is consumed by work enqueued on the current stream
+        before the next render call; a consumer on another stream or on the host must finish (or copy) before then."""
+        if slot is None:
+            slot = self._next_slot.get((width, height), 0)
+            self._next_slot[(width, height)] = slot ^ 1
         local = self.render_local(width, height, spp, max_depth, seed, sample_offset, slot)
         return self.combine(local, width, height, spp, slot)
 

@@ -289,6 +289,7 @@ class RayTracer:
         self._background = np.array([0.1, 0.1, 0.1])         # Scene::Scene()
         self._refits = 0
         self.refit_edits = True                              # set_scene of an unchanged object list refits instead of rebuilding
+        self.zero_copy_frames = False                        # render() returns a view of an internal page-locked frame (see render)
         self.rebuild_every = 64
         self._push_camera()
 
@@ -366,13 +367,18 @@ class RayTracer:
         return buf.numpy()
 
     def render(self, width: int, height: int, samples_per_pixel: int, max_depth: int) -> np.ndarray:
+        """RayTracer::render (binding.cpp:99).  Returns a float32 (H, W, 3) array that BELONGS TO THE CALLER, like the
+        reference's freshly allocated list: the frame is rendered into an internal page-locked buffer (what lets the kernel
+        push finished tiles across PCIe while it renders) and copied out once.  A host that consumes every frame at once --
+        the reference's does: np.array(result, dtype=np.float32), interaction.py:1304 -- can set ``zero_copy_frames = True``
+        and get the page-locked buffer itself: a view from a ring of three, overwritten by the third render after it."""
         with self._lock:
             self._camera.aspect_ratio = float(width) / float(height)
             out = self._ctx.render_host(width, height, samples_per_pixel, max_depth, seed=self.seed,
                                         sample_offset=self._sample_offset, out=self._host_frame(width, height))
             self._sample_offset = (self._sample_offset + samples_per_pixel) & 0xFFFFFFFF
             self._debug.render_count += 1
-            return out
+            return out if self.zero_copy_frames else out.copy()
 
     def select_object(self, x: float, y: float, width: int, height: int) -> int:
         with self._lock:

@@ -363,3 +363,85 @@ def test_mixed_radius_rays_device(ctx, golden_dir):
     assert (prim == ref).mean() >= 0.9995
     m = (prim == ref) & (prim >= 0)
     assert (np.abs(t[m] - g["t"][m]) / g["t"][m]).max() <= 1e-5
+
+
+# ------------------------------------------------------------------ round-2 API-contract cases
+@pytest.mark.parametrize("kernel", [-1, 0, 1, 2, 3, 4])
+@pytest.mark.parametrize("make", [scenes.default_scene, lambda: scenes.random_triangles(5_000, seed=12), scenes.cornell_box])
+def test_max_depth_zero_is_black_in_every_variant(ctx, kernel, make):
+    """RayTracer::trace_ray(depth <= 0) returns black before tracing anything (old/raytracer_core copy.cpp:212): a
+    max_depth-0 frame is all zeros -- resolved or as raw sums, whole frame or tiles -- whatever kernel is selected,
+    like the oracle's."""
+    s = make()
+    W, H = 96, 64
+    ctx.set_scene(s)
+    cam = s.camera.as_array(W / H)
+    ctx.set_camera_array(cam)
+    ctx.set_option("kernel", kernel)
+    try:
+        o = _oracle(s, cam)
+        oimg, _ = o.render(W, H, 2, 0, seed=9)
+        assert not oimg.any()
+        assert np.array_equal(ctx.render(W, H, 2, 0, seed=9).cpu().numpy(), oimg)
+        assert not ctx.render_sum(W, H, 2, 0, seed=9).cpu().numpy().any()
+        assert not ctx.render_host(W, H, 2, 0, seed=9).any()
+        tiles = ctx.render_tiles(W, H, 32, 32, 0, 1, 2, 0, seed=9)
+        assert not tiles.cpu().numpy().any()
+    finally:
+        ctx.set_option("kernel", -1)
+
+
+def test_two_streams_share_one_context(ctx):
+    """Context-owned scratch (work counter, wave buffers, sample planes, chunk schedule) is shared by all launches;
+    launches enqueued on DIFFERENT streams are ordered through an event, so frames rendered back to back on two
+    streams -- with no host synchronisation in between -- are each the frame a lone render gives."""
+    import torch
+    s = scenes.random_triangles(30_000, seed=21)
+    W, H = 480, 270
+    ctx.set_scene(s)
+    ctx.set_camera_array(s.camera.as_array(W / H))
+    want = {}
+    for spp, depth in [(1, 1), (4, 1), (2, 3)]:
+        want[(spp, depth)] = ctx.render(W, H, spp, depth, seed=31).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for rep in range(4):
+        for k, (spp, depth) in enumerate([(1, 1), (4, 1), (2, 3)]):
+            with torch.cuda.stream(s1 if (k + rep) % 2 == 0 else s2):
+                out = torch.empty((H, W, 3), dtype=torch.float32, device=ctx.device)
+                ctx.render(W, H, spp, depth, seed=31, out=out)
+                outs.append(((spp, depth), out))
+    host = ctx.render_host(W, H, 1, 1, seed=31)              # the library's own stream joins in
+    torch.cuda.synchronize()
+    for key, out in outs:
+        assert torch.equal(out, want[key]), key
+    assert np.array_equal(host, want[(1, 1)].cpu().numpy())
+
+
+def test_drop_in_render_returns_frames_the_caller_owns():
+    """binding.cpp:99 returns a fresh buffer per call: frames kept across later renders must not change (the shim
+    renders into a ring of page-locked buffers and copies out; zero_copy_frames opts out of the copy)."""
+    from pgr_raytracing_project_b200.raytracer_cpp import RayTracer, Scene, Sphere, Vector3
+    sc = Scene()
+    for k in range(3):
+        sp = Sphere()
+        sp.center = Vector3(k - 1.0, 0.0, -3.0)
+        sp.radius = 0.4
+        sp.object_id = k
+        sc.add_sphere(sp)
+    rt = RayTracer()
+    rt.set_scene(sc)
+    frames = [rt.render(128, 96, 1, 2) for _ in range(6)]
+    copies = [f.copy() for f in frames]
+    for _ in range(4):
+        rt.render(128, 96, 1, 2)
+    for f, c in zip(frames, copies):
+        assert np.array_equal(f, c)
+    assert not np.array_equal(frames[0], frames[1])          # successive calls continue the sample sequence
+    rt.zero_copy_frames = True
+    a = rt.render(128, 96, 1, 2)
+    rt.render(128, 96, 1, 2); rt.render(128, 96, 1, 2)
+    first = a.copy()
+    rt.render(128, 96, 1, 2)                                 # third render after `a`: the ring comes round
+    assert not np.array_equal(a, first)

@@ -586,7 +586,7 @@ def test_c4_ten_million_triangles():
 def test_sphere_twin_vs_v1_reference():
     """The 1M-sphere twin of C3 -- the only form of the headline workload the REAL reference can render: primary hit
     ids of the device against the unmodified v1 reference (oracle/_ref strict build, Scene::hit over ITS OWN pointer
-    BVH) on a 480x270 frame: identical ids, distances within 1e-5 relative."""
+    BVH) on a 480x270 frame: identical ids (but for grazing hits, see below), distances within 1e-5 relative."""
     from oracle import ref_v1
     if not ref_v1.available("strict"):
         pytest.skip("oracle/_ref not built (no /root/reference at build time)")
@@ -605,7 +605,23 @@ def test_sphere_twin_vs_v1_reference():
         ctx.close()
     rs = ref_v1.RefScene(s.center_radius, s.material8, s.object_id, s.background, flavour="strict")
     rid, rt_, _, _ = rs.primary(cam, W, H)
-    assert np.array_equal(ids, rid)
-    hit = rid >= 0
-    assert hit.mean() > 0.3
-    assert np.max(np.abs(t[hit] - rt_[hit]) / rt_[hit]) <= REL_T
+    # ids are identical except where the reference itself only GRAZES a sphere: v1 keeps the ray direction in double, the
+    # device rounds it to float32 once (the v2 contract), which moves the ray by ~1e-6 at this distance -- enough to flip a
+    # hit whose margin is 1e-7 of the radius (1 pixel of 129 600 on this frame).  Every differing pixel must be such a case.
+    diff = np.argwhere(ids != rid)
+    assert len(diff) <= 1e-4 * ids.size, len(diff)
+    for y, x in diff:
+        org, d = ref_v1.camera_get_ray(cam, (x + 0.5) / W, (y + 0.5) / H)
+        grazing = False
+        for k in (ids[y, x], rid[y, x]):
+            if k < 0:
+                continue
+            c = s.center_radius[k].astype(np.float64)
+            oc = org - c[:3]
+            b = oc @ d
+            dist = np.sqrt(max(oc @ oc - b * b, 0.0))
+            grazing |= abs(dist - c[3]) <= 1e-4 * c[3]
+        assert grazing, (y, x, ids[y, x], rid[y, x])
+    same = (ids == rid) & (rid >= 0)
+    assert same.mean() > 0.3
+    assert np.max(np.abs(t[same] - rt_[same]) / rt_[same]) <= REL_T

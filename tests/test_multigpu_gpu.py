@@ -46,9 +46,30 @@ def _worker(rank, world, port, out_dir):
             if rank == 0:
                 np.save(os.path.join(out_dir, f"{name}_{mode}.npy"), frame.cpu().numpy())
             dist.barrier()
+            # a pipeline of DIFFERENT consecutive frames with no host synchronisation in between (the renderer alternates
+            # its two shared buffers itself): every frame is consumed by a copy enqueued on the stream before the next
+            # render call -- what the lifetime rule of DistributedRenderer.render asks for -- while the other ranks run ahead
+            kept = []
+            for k in range(6):
+                frame = r.render(W, H, spp, depth, seed=5, sample_offset=k * spp)
+                if rank == 0:
+                    kept.append(frame.clone())
+            torch.cuda.synchronize()
+            if rank == 0:
+                np.save(os.path.join(out_dir, f"{name}_{mode}_seq.npy"), torch.stack(kept).cpu().numpy())
+            dist.barrier()
             r.close()
+            if mode == "peer":                                      # a closed renderer starts afresh (frames, sync words, counters)
+                frame = r.render(W, H, spp, depth, seed=5)
+                torch.cuda.synchronize()
+                if rank == 0:
+                    np.save(os.path.join(out_dir, f"{name}_reopened.npy"), frame.cpu().numpy())
+                dist.barrier()
+                r.close()
         if rank == 0:
             np.save(os.path.join(out_dir, f"{name}_full.npy"), full)
+            seq = [ctx.render(W, H, spp, depth, seed=5, sample_offset=k * spp).cpu().numpy() for k in range(6)]
+            np.save(os.path.join(out_dir, f"{name}_full_seq.npy"), np.stack(seq))
     ctx.close()
     dist.destroy_process_group()
 
@@ -60,7 +81,12 @@ def test_all_partition_modes_match_single_gpu(tmp_path):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     for name in ("tris_d1", "default_d4"):
         full = np.load(tmp_path / f"{name}_full.npy")
+        seq = np.load(tmp_path / f"{name}_full_seq.npy")
+        assert not np.array_equal(seq[0], seq[1])                   # consecutive frames really differ
         for mode in ("tiles", "peer", "peer+nccl"):
             assert np.array_equal(np.load(tmp_path / f"{name}_{mode}.npy"), full), (name, mode)   # bit-identical
+            assert np.array_equal(np.load(tmp_path / f"{name}_{mode}_seq.npy"), seq), (name, mode)
+        assert np.array_equal(np.load(tmp_path / f"{name}_reopened.npy"), full), name
         for mode in ("samples", "peer_samples", "peer_samples+nccl"):
             np.testing.assert_allclose(np.load(tmp_path / f"{name}_{mode}.npy"), full, atol=3e-6)  # re-associated sum
+            np.testing.assert_allclose(np.load(tmp_path / f"{name}_{mode}_seq.npy"), seq, atol=3e-6)
