@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rt.so")
-SOURCES = ["rt_api.cu", "rt_kernels.cu", "rt_wavefront.cu", "rt_lbvh.cu", "rt_refit.cu", "rt_display.cu", "rt_bvh.cpp"]
+SOURCES = ["rt_api.cu", "rt_kernels.cu", "rt_wavefront.cu", "rt_tiny.cu", "rt_lbvh.cu", "rt_refit.cu", "rt_display.cu", "rt_bvh.cpp"]
 HEADERS = ["rt_device.cuh", "rt_kernels.h", "rt_kernel_common.cuh", "rt_bvh.h", "rt_lbvh.h", "rt_refit.h", "rt_display.h", os.path.join("..", "..", "include", "b200rt.h")]
 
 
@@ -50,10 +50,16 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     """Every translation unit to an object file (in parallel; an object is reused while it is newer than its source,
     every header and this script), then one link.  The objects live in build/ (git-ignored)."""
+    out = os.environ.get("B200RT_LIB_OUT")                       # A/B builds (tools/): another library file, its own objects
+    if out:
+        return _build_to(os.path.abspath(out), os.path.join(HERE, "build", "alt_" + os.path.basename(out)), True, verbose)
     if not force and not needs_build():
         return LIB
+    return _build_to(LIB, os.path.join(HERE, "build"), force, verbose)
+
+
+def _build_to(LIB: str, objdir: str, force: bool, verbose: bool) -> str:
     from concurrent.futures import ThreadPoolExecutor
-    objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
     hdr_t = max(hdr_t, os.path.getmtime(os.path.abspath(__file__)))
@@ -67,11 +73,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     def compile_one(src):
         path = os.path.join(CSRC, src)
         obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
-        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_t):
-            return obj, "", 0
+        objlog = obj + ".log"                                    # ptxas -v output of this unit, kept next to a reused object
+        if not force and os.path.exists(obj) and os.path.exists(objlog) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_t):
+            return obj, open(objlog).read(), 0
         cmd = [nvcc_path()] + flags() + ["-c", path, "-o", obj]
         proc = subprocess.run(cmd, capture_output=True, text=True)
-        return obj, " ".join(cmd) + "\n" + proc.stdout + proc.stderr, proc.returncode
+        text = " ".join(cmd) + "\n" + proc.stdout + proc.stderr
+        with open(objlog, "w") as f:
+            f.write(text)
+        return obj, text, proc.returncode
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         results = list(ex.map(compile_one, SOURCES))

@@ -65,7 +65,7 @@ struct rt_ctx {
     double fov = 45.0, aspect = 1.333;
 
     // options
-    int integrator = 0, stats = 0, kernel = -1, refill = 8, leaf_vote = 8;
+    int integrator = 0, stats = 0, kernel = -1, refill = 8, leaf_vote = 8, tiny_threads = 256;
     int kernel_used = -1;                    // variant picked by the most recent tracing launch
     // auto choice for multi-bounce renders of tiny scenes (<= 64 primitives): which of the lock-step megakernel
     // (open scenes, short paths: the reference's default scene) and the wavefront (closed scenes, long paths: a
@@ -276,7 +276,7 @@ int ensure_bvh(rt_ctx* ctx) {
 SceneView scene_view(const rt_ctx* c) {
     SceneView v;
     v.nodes = c->d_nodes; v.prims = c->d_prims; v.cam_prims = c->d_cam_prims; v.slot_prim = c->d_slot_prim; v.mats = c->d_mats;
-    v.n_prims = (int)c->n; v.n_nodes = (int)c->n_nodes;
+    v.n_prims = (int)c->n; v.n_nodes = (int)c->n_nodes; v.n_mats = c->m;
     v.sane_extent = 0;
     if (c->n_nodes > 0) v.sane_extent = c->root_extent < 0x1p40f ? 1 : 0;      // NaN compares false
     v.bg_r = c->bg[0]; v.bg_g = c->bg[1]; v.bg_b = c->bg[2];
@@ -287,23 +287,29 @@ SceneView scene_view(const rt_ctx* c) {
 // tiny scenes are shading-bound and favour the lock-step megakernel; multi-bounce paths favour the
 // wavefront queues, with the coherent bounce 0 walked by packets; single-segment (camera-ray) work favours
 // the packet kernel.
+bool tiny_ok(const rt_ctx* c, int max_depth) {
+    return c->n > 0 && c->n <= kTinyMaxPrims && c->m > 0 && c->m <= kTinyMaxMats && max_depth >= 1 && max_depth <= kTinyMaxDepth;
+}
 int pick_kernel(const rt_ctx* c, int max_depth) {
     if (max_depth == 0) return 1;                                  // RayTracer::trace_ray(depth <= 0): no segment, black frame -- one kernel for it
-    if (c->kernel >= 0) {
+    if (c->kernel >= 0 && !(c->kernel == 5 && !tiny_ok(c, max_depth))) {
         if (c->kernel == 3 && max_depth != 1) return 0;        // packets handle camera rays only
         if (c->kernel == 4 && max_depth == 1) return 3;
         return c->kernel;
     }
+    if (tiny_ok(c, max_depth) && max_depth >= 2) return 5;     // whole scene in shared memory (timed against variant 1, see tunes())
     if (c->n <= 64) return 1;
     return max_depth >= 2 ? 4 : 3;
 }
 bool is_wavefront(int variant) { return variant == 2 || variant == 4; }
 
-constexpr int kTuneCandidates[2] = {1, 2};
+// candidates: the lock-step megakernel against the tiny-scene kernel (whole scene in shared memory, rt_tiny.cu) when the
+// scene is one it takes, else against the wavefront
 bool tunes(const rt_ctx* c, int max_depth) { return c->kernel < 0 && c->n > 0 && c->n <= 64 && max_depth >= 2; }
+int tune_candidate(const rt_ctx* c, int max_depth, int k) { return k == 0 ? 1 : (tiny_ok(c, max_depth) ? 5 : 2); }
 
 // Before a tuned render: collect the timing of the previous one, then say which variant runs now.
-int tune_begin(rt_ctx* c, cudaStream_t stream, double samples) {
+int tune_begin(rt_ctx* c, cudaStream_t stream, double samples, int max_depth) {
     if (!c->tune_ev0) { cudaEventCreate(&c->tune_ev0); cudaEventCreate(&c->tune_ev1); }
     if (c->tune_pending >= 0) {
         float ms = 0.0f;
@@ -313,11 +319,11 @@ int tune_begin(rt_ctx* c, cudaStream_t stream, double samples) {
         }
         c->tune_pending = -1;
     }
-    if (c->tune_state >= 2) return kTuneCandidates[c->tune_rate[1] < c->tune_rate[0] ? 1 : 0];
+    if (c->tune_state >= 2) return tune_candidate(c, max_depth, c->tune_rate[1] < c->tune_rate[0] ? 1 : 0);
     c->tune_pending = c->tune_state;
     c->tune_pending_samples = samples;
     cudaEventRecord(c->tune_ev0, stream);
-    return kTuneCandidates[c->tune_state];
+    return tune_candidate(c, max_depth, c->tune_state);
 }
 void tune_end(rt_ctx* c, cudaStream_t stream) { if (c->tune_pending >= 0) cudaEventRecord(c->tune_ev1, stream); }
 
@@ -335,6 +341,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
     cfg.band = BandSignal{nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 1, 1};
     cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr, 0};
     cfg.d_block_times = c->stats ? c->d_block_times : nullptr;
+    cfg.tiny_threads = c->tiny_threads;
     cfg.refill_below = c->refill;
     cfg.leaf_vote = c->leaf_vote;
     return cfg;
@@ -401,7 +408,7 @@ int attach_schedule(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm, const Camera
 // The camera-relative triangle table depends on the scene and on the camera POSITION only: a launch whose camera
 // sits where the table was built for (progressive batches, a turning camera) reuses it.
 void claim_cam_table(rt_ctx* ctx, LaunchCfg& cfg, const CameraBlock& cam) {
-    if (!ctx->is_tri) return;
+    if (!ctx->is_tri || cfg.variant == 5) return;              // the tiny-scene kernel keeps its own table in shared memory
     const bool same = ctx->cam_table_ok && ctx->cam_table_stream == cfg.stream && ctx->cam_table_pos[0] == cam.px && ctx->cam_table_pos[1] == cam.py && ctx->cam_table_pos[2] == cam.pz;
     cfg.cam_table_valid = same ? 1 : 0;
     ctx->cam_table_pos[0] = cam.px; ctx->cam_table_pos[1] = cam.py; ctx->cam_table_pos[2] = cam.pz;
@@ -411,6 +418,7 @@ void claim_cam_table(rt_ctx* ctx, LaunchCfg& cfg, const CameraBlock& cam) {
 // launches of one packet-kernel call: k_chunk_order (if scheduled) + k_cam_tris (triangles) + k_packet
 // kernels of one launch_render / launch_trace_primary call (every variant builds the camera table when it is stale)
 int render_launches(const rt_ctx* ctx, const LaunchCfg& cfg, int spp = 1) {
+    if (cfg.variant == 5) return 1;
     const int table = (ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0;
     if (cfg.variant != 3) return 1 + table;
     const int order = (cfg.sched.order && cfg.sched.reorder_frames > 0) ? 1 : 0;
@@ -774,6 +782,7 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
         return 0;
     }
     LaunchCfg cfg = launch_cfg(ctx, stream);
+    if (cfg.variant == 5) { cfg.variant = 1; ctx->kernel_used = 1; }   // the primary-hit query of a tiny scene: one ray per thread
     if (int rc = attach_schedule(ctx, cfg, tm, cam)) return rc;
     claim_cam_table(ctx, cfg, cam);
     CK(launch_trace_primary(scene_view(ctx), ctx->is_tri, cam, tm, d_prim, d_t, cfg));
@@ -950,7 +959,7 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
     const bool tuned = tunes(ctx, max_depth);
     if (tuned || is_wavefront(pick_kernel(ctx, max_depth))) { if (int rc = ensure_wave(ctx, task_count(tm), spp, max_depth)) return rc; }   // allocate outside the timed events
     ScratchOrder order(ctx, stream);
-    const int variant = tuned ? tune_begin(ctx, (cudaStream_t)stream, (double)width * height * spp) : pick_kernel(ctx, max_depth);
+    const int variant = tuned ? tune_begin(ctx, (cudaStream_t)stream, (double)width * height * spp, max_depth) : pick_kernel(ctx, max_depth);
     if (is_wavefront(variant)) {
         int nl = 0;
         LaunchCfg wcfg = launch_cfg(ctx, stream, max_depth, variant);
@@ -1218,13 +1227,14 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     std::string k(name);
     if (k == "integrator") { if (value != 0 && value != 1) return fail(ctx, "integrator must be 0 (v1) or 1 (v2)"); ctx->integrator = (int)value; }
     else if (k == "stats") ctx->stats = value != 0;
-    else if (k == "kernel") { if (value < -1 || value > 4) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront), 3 (camera-ray packets) or 4 (wavefront with packet bounce 0)"); ctx->kernel = (int)value; }
+    else if (k == "kernel") { if (value < -1 || value > 5) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront), 3 (camera-ray packets), 4 (wavefront with packet bounce 0) or 5 (tiny scenes: whole scene in shared memory; other scenes fall back to auto)"); ctx->kernel = (int)value; }
     else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
     else if (k == "overlap") { if (value < 0 || value > 2) return fail(ctx, "overlap must be 0 (render, then copy), 1 (region flags + DMA copies) or 2 (tile push)"); ctx->overlap = (int)value; }
     else if (k == "refit_limit") { if (value < 0 || value > 100000) return fail(ctx, "refit_limit must be 0 (never rebuild) or a percentage"); ctx->refit_limit = (int)value; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail(ctx, "builder must be 0 (reference median split, host) or 1 (LBVH, device)"); ctx->builder = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
     else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);
+    else if (k == "tiny_threads") { if (value != 128 && value != 256) return fail(ctx, "tiny_threads must be 128 or 256"); ctx->tiny_threads = (int)value; }
     else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
     else return fail(ctx, "rt_set_option: unknown option '" + k + "'");
     return 0;
@@ -1239,6 +1249,7 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "kernel") *value = ctx->kernel;
     else if (k == "kernel_used") *value = ctx->kernel_used;
     else if (k == "refill") *value = ctx->refill;
+    else if (k == "tiny_threads") *value = ctx->tiny_threads;
     else if (k == "overlap") *value = ctx->overlap;
     else if (k == "schedule") *value = ctx->schedule;
     else if (k == "leaf_vote") *value = ctx->leaf_vote;

@@ -24,6 +24,7 @@ namespace b200rt {
 constexpr float kTMin = 0.001f;   // old/raytracer_core copy.cpp:217
 constexpr float kTMax = 1e10f;
 constexpr int kStackDepth = 64;   // cpp_raytracer/raytracer_core.cpp:200
+constexpr int kTinyMaxPrims = 64, kTinyMaxMats = 64, kTinyMaxDepth = 8;   // scenes the tiny-scene kernel (rt_tiny.cu) takes
 constexpr int kTriStride = 3;     // float4 per triangle record: v0|prim, e1|material, e2|0 (48 B).  Measured and dropped: 64-byte
                                   // records read as two 256-bit loads (7.82 vs 7.78 ms on the C3 4-spp depth-4 frame, +33 % bytes)
 
@@ -42,6 +43,7 @@ struct SceneView {
     const float4* __restrict__ mats;       // 2 x float4 per material: albedo|metallic, roughness|emission
     int n_prims;
     int n_nodes;
+    int n_mats;
     int sane_extent;                       // every |coordinate| of the root box < 2^40 (octant slab test usable)
     float bg_r, bg_g, bg_b;
 };
@@ -177,6 +179,14 @@ __device__ __forceinline__ void tri_accept(Hit& h, float det, float un, float vn
         consider(h, __fdiv_rn(__fmul_rn(c, sg), det), prim, slot);
 }
 
+// The inside test of tri_accept alone (no distance): exactly its predicate, so that a kernel may first collect the
+// triangles a ray passes THROUGH (cheap, convergent) and run the full test -- division, closest-hit update -- only on those.
+__device__ __forceinline__ bool tri_inside(float det, float un, float vn) {
+    const float sg = det < 0.0f ? -1.0f : 1.0f;
+    det = __fmul_rn(det, sg); un = __fmul_rn(un, sg); vn = __fmul_rn(vn, sg);
+    return det > 0.0f && un >= 0.0f && vn >= 0.0f && __fadd_rn(un, vn) <= det;
+}
+
 // (e2 x e1 | e2.(s x e1)), (e2 x s | prim), (s x e1 | material) for origin (ox,oy,oz)
 __device__ __forceinline__ void cam_tri_record(float4 v0, float4 e1, float4 e2, float ox, float oy, float oz,
                                                float4& r0, float4& r1, float4& r2) {
@@ -195,15 +205,16 @@ __device__ __forceinline__ void test_cam_tri_records(const float4& r0, const flo
     const float vn = dot3(r.dx, r.dy, r.dz, r2.x, r2.y, r2.z);
     tri_accept(h, det, un, vn, r0.w, __float_as_int(r1.w), slot);
 }
+__device__ __forceinline__ bool cam_tri_inside(const float4& r0, const float4& r1, const float4& r2, const Ray& r) {
+    return tri_inside(dot3(r.dx, r.dy, r.dz, r0.x, r0.y, r0.z), dot3(r.dx, r.dy, r.dz, r1.x, r1.y, r1.z), dot3(r.dx, r.dy, r.dz, r2.x, r2.y, r2.z));
+}
 __device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ cam_prims, int slot, const Ray& r, Hit& h) {
     const float4* p = cam_prims + 3 * (size_t)slot;
     test_cam_tri_records(__ldg(p), __ldg(p + 1), __ldg(p + 2), slot, r, h);
 }
 
-// any-ray route
-__device__ __forceinline__ void test_tri_mt(const SceneView& sc, int slot, const Ray& r, Hit& h) {
-    const float4* p = sc.prims + kTriStride * (size_t)slot;
-    const float4 v0 = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
+// any-ray route (records v0 | prim, e1 | material, e2 | 0 already in registers)
+__device__ __forceinline__ void test_tri_mt_records(const float4& v0, const float4& e1, const float4& e2, int slot, const Ray& r, Hit& h) {
     float px, py, pz, qx, qy, qz;
     cross3(r.dx, r.dy, r.dz, e2.x, e2.y, e2.z, px, py, pz);
     const float det = dot3(e1.x, e1.y, e1.z, px, py, pz);
@@ -213,6 +224,52 @@ __device__ __forceinline__ void test_tri_mt(const SceneView& sc, int slot, const
     const float vn = dot3(r.dx, r.dy, r.dz, qx, qy, qz);
     const float c = dot3(e2.x, e2.y, e2.z, qx, qy, qz);
     tri_accept(h, det, un, vn, c, __float_as_int(v0.w), slot);
+}
+// inside test of test_tri_mt_records alone (the same det, u*det, v*det)
+__device__ __forceinline__ bool tri_mt_inside(const float4& v0, const float4& e1, const float4& e2, const Ray& r) {
+    float px, py, pz, qx, qy, qz;
+    cross3(r.dx, r.dy, r.dz, e2.x, e2.y, e2.z, px, py, pz);
+    const float det = dot3(e1.x, e1.y, e1.z, px, py, pz);
+    const float sx = __fsub_rn(r.ox, v0.x), sy = __fsub_rn(r.oy, v0.y), sz = __fsub_rn(r.oz, v0.z);
+    const float un = dot3(sx, sy, sz, px, py, pz);
+    cross3(sx, sy, sz, e1.x, e1.y, e1.z, qx, qy, qz);
+    const float vn = dot3(r.dx, r.dy, r.dz, qx, qy, qz);
+    return tri_inside(det, un, vn);
+}
+__device__ __forceinline__ void test_tri_mt(const SceneView& sc, int slot, const Ray& r, Hit& h) {
+    const float4* p = sc.prims + kTriStride * (size_t)slot;
+    test_tri_mt_records(__ldg(p), __ldg(p + 1), __ldg(p + 2), slot, r, h);
+}
+
+// the discriminant test of test_sphere_record alone
+__device__ __forceinline__ bool sphere_maybe(const float4& s, const Ray& r) {
+    double ocx = __dsub_rn((double)r.ox, (double)s.x), ocy = __dsub_rn((double)r.oy, (double)s.y),
+           ocz = __dsub_rn((double)r.oz, (double)s.z);
+    double dx = r.dx, dy = r.dy, dz = r.dz, rad = s.w;
+    double a = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    double half_b = __dadd_rn(__dadd_rn(__dmul_rn(ocx, dx), __dmul_rn(ocy, dy)), __dmul_rn(ocz, dz));
+    double c = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(ocx, ocx), __dmul_rn(ocy, ocy)), __dmul_rn(ocz, ocz)),
+                         __dmul_rn(rad, rad));
+    return !(__dsub_rn(__dmul_rn(half_b, half_b), __dmul_rn(a, c)) < 0.0);
+}
+
+// v1 Sphere::hit in double on the float32 ray / sphere (centre | radius), roots rounded to float32; `prim` is the
+// primitive number of slot `slot`
+__device__ __forceinline__ void test_sphere_record(const float4& s, int prim, int slot, const Ray& r, Hit& h) {
+    double ocx = __dsub_rn((double)r.ox, (double)s.x), ocy = __dsub_rn((double)r.oy, (double)s.y),
+           ocz = __dsub_rn((double)r.oz, (double)s.z);
+    double dx = r.dx, dy = r.dy, dz = r.dz, rad = s.w;
+    double a = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    double half_b = __dadd_rn(__dadd_rn(__dmul_rn(ocx, dx), __dmul_rn(ocy, dy)), __dmul_rn(ocz, dz));
+    double c = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(ocx, ocx), __dmul_rn(ocy, ocy)), __dmul_rn(ocz, ocz)),
+                         __dmul_rn(rad, rad));
+    double disc = __dsub_rn(__dmul_rn(half_b, half_b), __dmul_rn(a, c));
+    if (disc < 0.0) return;
+    double sq = __dsqrt_rn(disc);
+    float t = (float)__ddiv_rn(__dsub_rn(-half_b, sq), a);
+    if (!(t >= kTMin && t <= h.t)) t = (float)__ddiv_rn(__dadd_rn(-half_b, sq), a);
+    if (!(t >= kTMin && t <= h.t)) return;
+    consider(h, t, prim, slot);
 }
 
 // cam: this ray is a camera ray (table route for triangles)
@@ -518,16 +575,21 @@ __device__ __forceinline__ void packet_intersect(const SceneView& sc, const floa
 }
 
 // ------------------------------------------------------------------------------- shading
-template <bool TRI>
+// SMEM: the SceneView's prims / mats pointers point into SHARED memory (the tiny-scene kernel stages the whole scene
+// there, rt_tiny.cu): plain loads (LDS) instead of ld.global.nc.
+template <bool SMEM>
+__device__ __forceinline__ float4 ld4(const float4* p) { return SMEM ? *p : __ldg(p); }
+
+template <bool TRI, bool SMEM = false>
 __device__ __forceinline__ void shading_normal(const SceneView& sc, const Hit& h, const Ray& r, float px,
                                                float py, float pz, float& nx, float& ny, float& nz) {
     if (TRI) {
         const float4* p = sc.prims + kTriStride * (size_t)h.slot;
-        float4 e1 = __ldg(p + 1), e2 = __ldg(p + 2);
+        float4 e1 = ld4<SMEM>(p + 1), e2 = ld4<SMEM>(p + 2);
         cross3(e1.x, e1.y, e1.z, e2.x, e2.y, e2.z, nx, ny, nz);
         normalize3(nx, ny, nz);
     } else {
-        float4 s = __ldg(sc.prims + h.slot);
+        float4 s = ld4<SMEM>(sc.prims + h.slot);
         float inv = __fdiv_rn(1.0f, s.w);                           // raytracer_core.h:210
         nx = __fmul_rn(__fsub_rn(px, s.x), inv); ny = __fmul_rn(__fsub_rn(py, s.y), inv); nz = __fmul_rn(__fsub_rn(pz, s.z), inv);
     }
@@ -545,7 +607,7 @@ __device__ __forceinline__ void unit_sphere(uint32_t pixel, uint32_t sample, uin
 
 // Scatter at a hit (both integrators).  Returns false when the path ends here.
 // ctl = the control draws of this bounce: .z Russian roulette, .w metal selection.
-template <bool TRI>
+template <bool TRI, bool SMEM = false>
 __device__ __forceinline__ bool scatter(const SceneView& sc, const Hit& h, Ray& r, int integrator, int b,
                                         int max_depth, uint4 ctl, float4 m0, float4 m1, uint32_t pixel,
                                         uint32_t sample, uint32_t k0, uint32_t k1, float& tr, float& tg, float& tb) {
@@ -568,7 +630,7 @@ __device__ __forceinline__ bool scatter(const SceneView& sc, const Hit& h, Ray& 
     }
     float px = __fmaf_rn(r.dx, h.t, r.ox), py = __fmaf_rn(r.dy, h.t, r.oy), pz = __fmaf_rn(r.dz, h.t, r.oz);
     float nx, ny, nz;
-    shading_normal<TRI>(sc, h, r, px, py, pz, nx, ny, nz);
+    shading_normal<TRI, SMEM>(sc, h, r, px, py, pz, nx, ny, nz);
     float ux, uy, uz;
     unit_sphere(pixel, sample, (uint32_t)b, k0, k1, ux, uy, uz);
     float dx, dy, dz;
@@ -586,9 +648,9 @@ __device__ __forceinline__ bool scatter(const SceneView& sc, const Hit& h, Ray& 
     return true;
 }
 
-template <bool TRI>
+template <bool TRI, bool SMEM = false>
 __device__ __forceinline__ int material_row(const SceneView& sc, const Hit& h) {
-    if (TRI) return __float_as_int(__ldg(sc.prims + kTriStride * (size_t)h.slot + 1).w);
+    if (TRI) return __float_as_int(ld4<SMEM>(sc.prims + kTriStride * (size_t)h.slot + 1).w);
     return h.prim;
 }
 

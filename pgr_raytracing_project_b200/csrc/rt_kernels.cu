@@ -637,6 +637,8 @@ cudaError_t launch_render(const SceneView& sc, bool is_tri, const CameraBlock& c
     if (n_work == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), cfg.stream);
     if (e != cudaSuccess) return e;
+    if (cfg.variant == 5)                                           // the tiny-scene kernel builds its own table in shared memory
+        return launch_tiny(sc, is_tri, sc.n_mats, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, d_out, cfg);
     if (is_tri && !cfg.cam_table_valid && (e = launch_cam_tris(sc, cam, cfg)) != cudaSuccess) return e;   // bounce 0 uses the table
     bool st = cfg.d_stats != nullptr;
     if (cfg.variant == 3 && max_depth == 1) {

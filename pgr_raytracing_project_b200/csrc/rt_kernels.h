@@ -76,7 +76,8 @@ struct LaunchCfg {
     unsigned long long* d_stats;             // [rays, segments, node_records, prim_tests] or nullptr
     int variant;                             // 0 = k_path (lane continuation), 1 = simple per-pixel megakernel, 2 = wavefront,
                                              // 3 = k_packet (camera rays: warp = packet with one shared stack),
-                                             // 4 = wavefront with bounce 0 by packets (k_wf_packet0)
+                                             // 4 = wavefront with bounce 0 by packets (k_wf_packet0),
+                                             // 5 = k_tiny (whole scene in shared memory, CTA-local wavefront; rt_tiny.cu)
     float4* d_cam_prims;                     // camera-relative triangle records (3 x float4 per slot)
     int cam_table_valid;                     // the table already holds this scene + camera position: skip k_cam_tris
     BandSignal band;                         // cnt == nullptr: no signalling
@@ -84,6 +85,7 @@ struct LaunchCfg {
     float4* d_planes;                        // item mode of k_packet (multi-sample frames): sample planes, plane_batch x tasks
     int plane_batch;                         // samples per batch the planes buffer holds for this tile map (0: loop mode)
     unsigned long long* d_block_times;       // debug (instrumented k_packet only): [2 * work item] = globaltimer start, end; or nullptr
+    int tiny_threads;                        // k_tiny: threads per CTA (256 or 128)
     int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes
     int leaf_vote;                           // phase voting: leaf step when >= this many lanes hold a leaf
 };
@@ -103,6 +105,10 @@ cudaError_t launch_wavefront(const SceneView& sc, bool is_tri, bool aov, const C
                              int spp, int max_depth, int integrator, uint64_t seed, uint32_t sample_offset, int resolve,
                              float* d_out, int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb,
                              int* n_launches);
+// tiny scenes (rt_tiny.cu): the whole scene staged in shared memory, brute-force closest hit, CTA-local wavefront
+bool tiny_eligible(const SceneView& sc, int n_mats, int max_depth);
+cudaError_t launch_tiny(const SceneView& sc, bool is_tri, int n_mats, const CameraBlock& cam, const TileMap& tm, int spp, int max_depth,
+                        int integrator, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out, const LaunchCfg& cfg);
 cudaError_t launch_cam_tris(const SceneView& sc, const CameraBlock& cam, const LaunchCfg& cfg);   // per-frame camera-relative triangle table
 int packet_chunks(const TileMap& tm, int items_per_block);   // chunks k_packet cuts this tile map into (ChunkSchedule sizes)
 cudaError_t launch_trace_primary(const SceneView& sc, bool is_tri, const CameraBlock& cam, const TileMap& tm,

@@ -366,7 +366,7 @@ def test_mixed_radius_rays_device(ctx, golden_dir):
 
 
 # ------------------------------------------------------------------ round-2 API-contract cases
-@pytest.mark.parametrize("kernel", [-1, 0, 1, 2, 3, 4])
+@pytest.mark.parametrize("kernel", [-1, 0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("make", [scenes.default_scene, lambda: scenes.random_triangles(5_000, seed=12), scenes.cornell_box])
 def test_max_depth_zero_is_black_in_every_variant(ctx, kernel, make):
     """RayTracer::trace_ray(depth <= 0) returns black before tracing anything (old/raytracer_core copy.cpp:212): a

@@ -20,13 +20,14 @@ pytestmark = pytest.mark.gpu
 REL_T = 1e-5
 
 
-@pytest.fixture(scope="module", params=[0, 1, 2, 3, 4, -1], ids=["k_path", "simple", "wavefront", "packet", "wavefront_packet0", "auto"])
+@pytest.fixture(scope="module", params=[0, 1, 2, 3, 4, 5, -1], ids=["k_path", "simple", "wavefront", "packet", "wavefront_packet0", "tiny", "auto"])
 def ctx(request):
     """Every tracing kernel must meet every bar: 0 = persistent path kernel with lane-level
     continuation, 1 = simple one-pixel-per-thread megakernel, 2 = wavefront (generate / trace / shade /
     accumulate kernels with compacted ray queues), 3 = camera-ray packets (warp = 8x4 pixel packet with
     one shared stack; max_depth 1 and the AOV, k_path otherwise), 4 = wavefront whose bounce 0 is generated and
-    traced by packets, -1 = the library's own choice."""
+    traced by packets, 5 = the tiny-scene kernel (whole scene in shared memory, brute force, CTA-local wavefront; scenes it
+    does not take fall back to the library's choice), -1 = the library's own choice."""
     from pgr_raytracing_project_b200.context import RenderContext
     c = RenderContext(0)
     c.set_option("kernel", request.param)
@@ -56,7 +57,9 @@ def _check_counters(ctx, st, o_nodes, o_prims):
     """Per-ray kernels visit nodes in the oracle's near-first order => identical work counters (the
     roofline's bytes/ray inputs).  The packet kernel counts what a 32-ray packet fetched once, which
     can only be less than the 32 separate walks."""
-    if ctx.get_option("kernel_used") in (3, 4):
+    if ctx.get_option("kernel_used") == 5:        # tiny scenes: brute force out of shared memory, every primitive per segment
+        assert st["node_records"] == 0 and st["prim_tests"] == st["segments"] * ctx.get_option("n_prims")
+    elif ctx.get_option("kernel_used") in (3, 4):
         assert 0 < st["node_records"] <= o_nodes and st["prim_tests"] <= o_prims
     else:
         assert st["node_records"] == o_nodes and st["prim_tests"] == o_prims
