@@ -479,6 +479,7 @@ def main():
         alone = ctx.render(W, H, spp_total, MAX_DEPTH, RENDER_SEED, k_last * spp_total)
         torch.cuda.synchronize()
         frame_matches_1gpu = bool(torch.equal(got, alone))
+        alone_np = alone.cpu().numpy()
         del alone
     frame0 = None
     if world == 1:
@@ -524,13 +525,13 @@ def main():
         if world == 1:
             ctx.render_host(W, H, SPP_PER_GPU, MAX_DEPTH, RENDER_SEED, k, out=host_np)   # frame out
         else:
-            frame = step(k)
-            if rank == 0:
-                host.copy_(frame, non_blocking=True)
+            renderer.render_host(W, H, spp_total, MAX_DEPTH, RENDER_SEED, k * spp_total)   # rank 0 returns when all ranks' tiles have landed
             torch.cuda.synchronize()
 
     e2e_api = ("rt_set_camera + rt_render_host (pinned host framebuffer; the kernel pushes finished tiles into it)" if world == 1 else
-               "DistributedRenderer.render + copy of the resolved frame to pinned host memory on rank 0")
+               "rt_set_camera + DistributedRenderer.render_host (rt_render_tiles_host): every rank's GPU stores its own tiles of the N-spp frame "
+               "straight into ONE page-locked host frame shared by all processes (/dev/shm + cudaHostRegister), each over its own PCIe "
+               "link; rank 0 returns when every rank's flag word has arrived")
     for k in range(3):
         e2e_step(k)
     barrier()
@@ -547,6 +548,13 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = rays_total / float(e2e_t.item()) / 1e6
+    host_frame_matches_1gpu = None
+    if world > 1:                                       # the frame the e2e path assembled in host memory, checked like the device frame
+        hf = renderer.render_host(W, H, spp_total, MAX_DEPTH, RENDER_SEED, k_last * spp_total)
+        torch.cuda.synchronize()
+        if rank == 0:
+            host_frame_matches_1gpu = bool(np.array_equal(hf, alone_np))
+        barrier()
 
     # ---- the GUI's batch on the same scene, STRONG scaling (fixed work split over N GPUs): C3 scene, 1920x1080, 8 spp,
     # max_depth 4 (interaction.py:1294-1298 calls render(W,H,8,4)); device-timed, max over ranks, L2 flushed
@@ -622,7 +630,7 @@ def main():
                                   "note": "per-step CUDA-event times; each figure is the max over ranks"},
             "config": bench_config(world, exchange_mode, barrier_mode),
             "scene": {"bvh_nodes": int(len(nodes)), "host_bvh_build_plus_upload_s": round(build_s, 2)},
-            "frame_matches_1gpu": frame_matches_1gpu,
+            "frame_matches_1gpu": frame_matches_1gpu, "host_frame_matches_1gpu": host_frame_matches_1gpu,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 112, "d2h_bytes_per_step": W * H * 3 * 4,
                     "ms_per_step": float(e2e_t.item()) / args.steps * 1e3, "api": e2e_api},
@@ -651,7 +659,7 @@ def main():
     barrier()
     if world > 1:
         dist.destroy_process_group()
-    if rank == 0 and (frame_matches_1gpu is False or (out.get("cpu_baseline") or {}).get("frame_matches_gpu") is False):
+    if rank == 0 and (frame_matches_1gpu is False or host_frame_matches_1gpu is False or (out.get("cpu_baseline") or {}).get("frame_matches_gpu") is False):
         log("FRAME MISMATCH: the timed frame differs from the 1-GPU / oracle frame")
         sys.exit(3)
 

@@ -162,6 +162,20 @@ int rt_frame_close(rt_ctx* ctx, float* d_peer_frame);
  * for lost: the waiting kernels trap, so every waiting process fails at its next CUDA call rather than reading an
  * incomplete frame.  width / height / planes as given to rt_frame_alloc. */
 int rt_frame_sync(rt_ctx* ctx, float* d_frame, int width, int height, int planes, int world, uint64_t epoch, void* stream);
+/* HOST frames shared between the processes of one node -- the multi-GPU form of rt_render_host.  The frame lives in
+ * host memory that every process maps (POSIX shared memory, a file under /dev/shm ...); each process page-locks it
+ * and gets a device alias (rt_host_register: cudaHostRegister portable + mapped), and rt_render_tiles_host renders
+ * this rank's (skew-dealt, see rt_render_tiles_frame) 32x32 tiles and lets the GPU store them straight into the
+ * shared host frame over ITS OWN PCIe link: no gather on a display GPU, no serial device->host copy; N GPUs move the
+ * frame N times as fast.  When the last tile of the rank has been stored the GPU writes `epoch` into the rank's flag
+ * word (host memory as well, d_flag = its device alias); the consumer waits for all ranks' words with rt_host_wait
+ * (a spin on host memory, no CUDA call).  The call only enqueues work on `stream`. */
+int rt_host_register(rt_ctx* ctx, void* h_ptr, uint64_t bytes, void** d_alias);
+int rt_host_unregister(rt_ctx* ctx, void* h_ptr);
+int rt_render_tiles_host(rt_ctx* ctx, int width, int height, int rank, int world, int spp, int max_depth, uint64_t seed,
+                         uint32_t sample_offset, float* d_host_frame, uint32_t* d_flag, uint32_t epoch, void* stream);
+/* 0 when all n flag words equal `epoch`; 2 after timeout_s seconds. */
+int rt_host_wait(const volatile uint32_t* h_flags, int n, uint32_t epoch, double timeout_s);
 /* Full frame, raw radiance sums (no mean / gamma / clamp): the per-rank partial of a sample-range
  * partition; sum the partials (e.g. ncclReduce) and finish with rt_resolve. */
 int rt_render_sum(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed,

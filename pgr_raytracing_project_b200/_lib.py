@@ -16,7 +16,7 @@ SYMBOLS = [
     "rt_render_host", "rt_accumulate", "rt_tonemap_u8", "rt_set_option", "rt_get_option", "rt_get_stats",
     "rt_reset_stats", "rt_build_bvh_host", "rt_render_sum", "rt_resolve", "rt_render_tiles_frame", "rt_frame_alloc",
     "rt_frame_free", "rt_frame_open", "rt_frame_close", "rt_resolve_planes", "rt_display_u8", "rt_update_geometry",
-    "rt_update_materials", "rt_frame_sync",
+    "rt_update_materials", "rt_frame_sync", "rt_host_register", "rt_host_unregister", "rt_render_tiles_host", "rt_host_wait",
 ]
 
 
@@ -60,6 +60,10 @@ def load():
         "rt_set_background": (ci, [vp, fp]),
         "rt_update_geometry": (ci, [vp, fp, i64]),
         "rt_frame_sync": (ci, [vp, vp, ci, ci, ci, ci, u64, vp]),
+        "rt_host_register": (ci, [vp, vp, u64, C.POINTER(vp)]),
+        "rt_host_unregister": (ci, [vp, vp]),
+        "rt_render_tiles_host": (ci, [vp, ci, ci, ci, ci, ci, ci, u64, u32, vp, vp, u32, vp]),
+        "rt_host_wait": (ci, [vp, ci, u32, C.c_double]),
         "rt_update_materials": (ci, [vp, fp, ci]),
         "rt_build_bvh": (ci, [vp, ci]),
         "rt_get_bvh": (ci, [vp, vp, C.POINTER(i64), ip]),

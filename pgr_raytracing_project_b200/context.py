@@ -266,6 +266,29 @@ class RenderContext:
     def frame_free(self, ptr: int):
         self._ck(self.L.rt_frame_free(self.h, C.c_void_p(ptr)))
 
+    # ------------------------------------------------------------------ host frames shared across processes
+    def host_register(self, address: int, nbytes: int) -> int:
+        """Page-lock host memory [address, address + nbytes) for this process's GPU; -> its device alias."""
+        d = C.c_void_p()
+        self._ck(self.L.rt_host_register(self.h, C.c_void_p(address), nbytes, C.byref(d)))
+        return int(d.value)
+
+    def host_unregister(self, address: int):
+        self._ck(self.L.rt_host_unregister(self.h, C.c_void_p(address)))
+
+    def render_tiles_host(self, width: int, height: int, rank: int, world: int, spp: int, max_depth: int, seed: int,
+                          sample_offset: int, d_host_frame: int, d_flag: int, epoch: int):
+        """rank's tiles rendered and stored by the GPU into the shared page-locked host frame (device alias
+        `d_host_frame`); `epoch` lands in the flag word (device alias `d_flag`) when they are all there."""
+        self._ck(self.L.rt_render_tiles_host(self.h, width, height, rank, world, spp, max_depth, C.c_uint64(seed),
+                                             C.c_uint32(sample_offset), C.c_void_p(d_host_frame), C.c_void_p(d_flag),
+                                             C.c_uint32(epoch), self._stream()))
+
+    def host_wait(self, flags_address: int, n: int, epoch: int, timeout_s: float = 20.0):
+        rc = self.L.rt_host_wait(C.c_void_p(flags_address), n, C.c_uint32(epoch), float(timeout_s))
+        if rc != 0:
+            raise B200RTError("rt_host_wait: a rank did not deliver its tiles in time" if rc == 2 else "rt_host_wait: bad arguments")
+
     def untile(self, width: int, height: int, tile_w: int, tile_h: int, n_ranks: int, tiles: torch.Tensor,
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if out is None:

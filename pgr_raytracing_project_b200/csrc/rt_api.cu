@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -944,6 +945,63 @@ int rt_frame_sync(rt_ctx* ctx, float* d_frame, int width, int height, int planes
     CK(launch_frame_sync(words, (unsigned long long)world * epoch, (cudaStream_t)stream));
     ctx->launches += 1;
     return 0;
+}
+
+// ---- host frames shared between the processes of one node (see b200rt.h)
+int rt_host_register(rt_ctx* ctx, void* h_ptr, uint64_t bytes, void** d_alias) {
+    if (!ctx || !h_ptr || !d_alias || bytes == 0) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaHostRegister(h_ptr, (size_t)bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    void* d = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&d, h_ptr, 0);
+    if (e != cudaSuccess) { cudaHostUnregister(h_ptr); return cuda_fail(ctx, "cudaHostGetDevicePointer", e); }
+    *d_alias = d;
+    return 0;
+}
+
+int rt_host_unregister(rt_ctx* ctx, void* h_ptr) {
+    if (!ctx || !h_ptr) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    DeviceGuard g(ctx->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaHostUnregister(h_ptr));
+    return 0;
+}
+
+int rt_render_tiles_host(rt_ctx* ctx, int width, int height, int rank, int world, int spp, int max_depth, uint64_t seed,
+                         uint32_t sample_offset, float* d_host_frame, uint32_t* d_flag, uint32_t epoch, void* stream) {
+    if (!ctx) return 1;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    if (int rc = check_frame(ctx, width, height)) return rc;
+    if (rank < 0 || world <= 0 || rank >= world || !d_host_frame || !d_flag) return fail(ctx, "rt_render_tiles_host: bad arguments");
+    if (((uintptr_t)d_host_frame & 15u) != 0) return fail(ctx, "rt_render_tiles_host: the host frame must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    const size_t need = (size_t)width * height * 3;
+    if (need > ctx->fb_floats) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(ctx->d_fb); ctx->d_fb = nullptr; ctx->fb_floats = 0;
+        CK(cudaMalloc(&ctx->d_fb, need * sizeof(float)));
+        ctx->fb_floats = need;
+    }
+    if (int rc = render_tiles(ctx, width, height, 32, 32, rank, world, spp, max_depth, seed, sample_offset, 1, ctx->d_fb, stream, 1)) return rc;
+    TileMap tm = full_frame_map(width, height);
+    tm.first_tile = rank; tm.tile_stride = world; tm.skew = 1;
+    tm.n_local_tiles = rank < tm.n_tiles ? (tm.n_tiles - rank + world - 1) / world : 0;
+    CK(launch_push_tiles(tm, ctx->d_fb, d_host_frame, d_flag, epoch, ctx->d_work_counter + 8, (cudaStream_t)stream));
+    ctx->launches += 1;
+    return 0;
+}
+
+int rt_host_wait(const volatile uint32_t* h_flags, int n, uint32_t epoch, double timeout_s) {
+    if (!h_flags || n <= 0) return 1;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        bool all = true;
+        for (int k = 0; k < n; ++k) all = all && h_flags[k] == epoch;
+        if (all) { std::atomic_thread_fence(std::memory_order_acquire); return 0; }
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) return 2;
+    }
 }
 
 static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_depth, uint64_t seed, uint32_t sample_offset,

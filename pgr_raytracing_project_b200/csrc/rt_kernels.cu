@@ -314,6 +314,28 @@ __device__ __noinline__ void push_tile(const float* __restrict__ fb, float* __re
     }
 }
 
+// rt_render_tiles_host: one warp per tile of this launch's tile map (32x32 tiles): the tile's rows from the device frame
+// (L2) into the shared page-locked host frame, 384 contiguous bytes per row; the last warp to finish publishes `epoch`.
+__global__ void __launch_bounds__(256)
+k_push_tiles(const __grid_constant__ TileMap tm, const float* __restrict__ fb, float* __restrict__ host, unsigned int* flag,
+             unsigned int epoch, unsigned int* cnt) {
+    const int lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * (blockDim.x >> 5);
+    for (int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); k < tm.n_local_tiles; k += n_warps) {
+        const int tile = tm.first_tile + k * tm.tile_stride;
+        const int ty = tile / tm.tiles_x;
+        int tx = tile - ty * tm.tiles_x;
+        if (tm.skew) tx = (tx + tm.skew * ty) % tm.tiles_x;
+        push_tile(fb, host, tm.width, tm.height, ty, tx, lane);
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0 && atomicAdd(cnt, 1u) + 1u == (unsigned)n_warps) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(flag) = epoch;
+    }
+}
+
 // ptxas settles at 48 registers = 5 CTAs of 256 threads per SM, the measured optimum: forcing 40 / 32 registers (6 / 8
 // CTAs) spills and is 3 % / 18 % slower, and anything that pushes the kernel to 64 registers (4 CTAs) costs 4-5 % --
 // which is why the final pixel store here is the plain one and not warp_store_rgb
@@ -705,6 +727,17 @@ cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, i
     double total = (double)n_old + (double)n_batch;
     float w_old = (float)((double)n_old / total), w_new = (float)((double)n_batch / total);
     k_accumulate<<<elementwise_grid(n), 256, 0, stream>>>(d_batch, d_accum, n, w_old, w_new, n_old == 0 ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_push_tiles(const TileMap& tm, const float* d_fb, float* d_host, unsigned int* d_flag, unsigned int epoch,
+                              unsigned int* d_cnt, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    int grid = (tm.n_local_tiles + 7) / 8;
+    if (grid < 1) grid = 1;
+    if (grid > 148 * 4) grid = 148 * 4;
+    k_push_tiles<<<grid, 256, 0, stream>>>(tm, d_fb, d_host, d_flag, epoch, d_cnt);
     return cudaGetLastError();
 }
 

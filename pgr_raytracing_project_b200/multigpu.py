@@ -115,6 +115,7 @@ class DistributedRenderer:
         self._shared = {}          # (W, H, slot) -> (pointer, torch view or None, owner?)
         self._next_slot = {}       # (W, H) -> slot of the next frame when the caller does not name one (0 / 1 alternating)
         self._token = None         # one-element tensor of the NCCL barrier
+        self._host = {}            # (W, H, slot) -> shared page-locked host frame (render_host)
 
     def _buf(self, key, shape):
         import torch
@@ -165,6 +166,14 @@ class DistributedRenderer:
         self._shared = {}
         self._epoch = {}
         self._next_slot = {}
+        for ent in self._host.values():
+            self.ctx.host_unregister(ent["address"])
+            ent["frame"] = ent["buf"] = None
+            try:
+                ent["mm"].close()
+            except BufferError:                             # the caller still holds a frame: the mapping goes with it
+                pass
+        self._host = {}
 
     def render(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0, slot=None):
         """tiles: the resolved frame on every rank.  samples / peer modes: the resolved frame on rank 0 (None elsewhere).
@@ -182,6 +191,71 @@ class DistributedRenderer:
             self._next_slot[(width, height)] = slot ^ 1
         local = self.render_local(width, height, spp, max_depth, seed, sample_offset, slot)
         return self.combine(local, width, height, spp, slot)
+
+    # ------------------------------------------------------------------ frames assembled in shared HOST memory
+    def _host_frame(self, width: int, height: int, slot: int):
+        """The page-locked host frame for (W, H, slot), mapped into every process: a file under /dev/shm created by rank 0,
+        mmap'ed by all ranks and registered with each rank's own GPU (rt_host_register).  Layout: H*W*3 floats, then (4 KiB
+        aligned) one flag word per rank.  Collective on first use."""
+        import mmap
+        import os
+        import torch.distributed as dist
+        key = (width, height, slot)
+        ent = self._host.get(key)
+        if ent is not None:
+            return ent
+        frame_bytes = width * height * 3 * 4
+        flags_off = (frame_bytes + 4095) & ~4095
+        total = flags_off + 4096
+        name = [None]
+        if self.rank == 0:
+            name[0] = "/dev/shm/b200rt_%d_%d_%dx%d_%d" % (os.getpid(), id(self) & 0xFFFFFF, width, height, slot)
+            fd = os.open(name[0], os.O_CREAT | os.O_RDWR | os.O_EXCL, 0o600)
+            os.ftruncate(fd, total)
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=0, group=self.group)
+        if self.rank != 0:
+            fd = os.open(name[0], os.O_RDWR)
+        mm = mmap.mmap(fd, total)
+        os.close(fd)
+        buf = np.frombuffer(mm, dtype=np.uint8)
+        address = buf.ctypes.data
+        if self.world > 1:
+            dist.barrier(group=self.group)                  # everybody has the file open: the name can go
+        if self.rank == 0:
+            os.unlink(name[0])
+        alias = self.ctx.host_register(address, total)
+        ent = {"mm": mm, "buf": buf, "address": address, "alias": alias, "flags_off": flags_off, "epoch": 0,
+               "frame": buf[:frame_bytes].view(np.float32).reshape(height, width, 3)}
+        self._host[key] = ent
+        return ent
+
+    def render_host(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0, slot=None):
+        """The multi-GPU form of RenderContext.render_host: the frame is assembled in shared page-locked HOST memory, every
+        rank's GPU storing its own tiles there over its own PCIe link (no gather on a display GPU, no serial device->host
+        copy).  Returns the (H, W, 3) float32 numpy frame on rank 0 once every rank's tiles have landed (None on the other
+        ranks, whose call only enqueues).  Frames alternate between two host buffers like render()'s: the returned array
+        is overwritten by the render_host call after the next one."""
+        ctx = self.ctx
+        if slot is None:
+            slot = self._next_slot.get(("host", width, height), 0)
+            self._next_slot[("host", width, height)] = slot ^ 1
+        ent = self._host_frame(width, height, slot)
+        ent["epoch"] += 1
+        # back-pressure: rank 0 entering the call for this buffer's frame number `epoch` says that the buffer's previous
+        # frame has been consumed (the lifetime rule above); the other ranks, which never wait for anything else and
+        # could run frames ahead, do not store into the buffer before that (release word = flag word 64)
+        release = ent["buf"][ent["flags_off"] + 256:ent["flags_off"] + 260].view(np.uint32)
+        if self.rank == 0:
+            release[0] = ent["epoch"]
+        else:
+            ctx.host_wait(ent["address"] + ent["flags_off"] + 256, 1, ent["epoch"])
+        ctx.render_tiles_host(width, height, self.rank, self.world, spp, max_depth, seed, sample_offset, ent["alias"],
+                              ent["alias"] + ent["flags_off"] + 4 * self.rank, ent["epoch"])
+        if self.rank != 0:
+            return None
+        ctx.host_wait(ent["address"] + ent["flags_off"], self.world, ent["epoch"])
+        return ent["frame"]
 
     def render_local(self, width: int, height: int, spp: int, max_depth: int, seed: int = 0, sample_offset: int = 0,
                      slot: int = 0):

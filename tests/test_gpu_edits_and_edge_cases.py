@@ -445,3 +445,40 @@ def test_drop_in_render_returns_frames_the_caller_owns():
     first = a.copy()
     rt.render(128, 96, 1, 2)                                 # third render after `a`: the ring comes round
     assert not np.array_equal(a, first)
+
+
+def test_shared_host_frame_assembled_by_ranks(ctx):
+    """rt_render_tiles_host on one GPU standing in for 1, 2 and 3 ranks: every "rank" stores its skew-dealt tiles into one
+    page-locked host frame (plain mmap'ed memory registered with rt_host_register) and raises its flag word; the
+    assembled frame is the one-shot render, for camera-ray frames (packet kernel, 1 and 3 spp) and multi-bounce frames."""
+    import mmap
+    import torch
+    s = scenes.random_triangles(30_000, seed=23)
+    W, H = 200, 136                                              # ragged: 7 x 5 tiles, the last column / row partial
+    ctx.set_scene(s)
+    ctx.set_camera_array(s.camera.as_array(W / H))
+    frame_bytes = W * H * 3 * 4
+    flags_off = (frame_bytes + 4095) & ~4095
+    mm = mmap.mmap(-1, flags_off + 4096)
+    buf = np.frombuffer(mm, dtype=np.uint8)
+    address = buf.ctypes.data
+    alias = ctx.host_register(address, flags_off + 4096)
+    try:
+        frame = buf[:frame_bytes].view(np.float32).reshape(H, W, 3)
+        flags = buf[flags_off:flags_off + 64].view(np.uint32)
+        epoch = 0
+        for spp, depth in [(1, 1), (3, 1), (2, 3)]:
+            want = ctx.render(W, H, spp, depth, seed=17, sample_offset=2).cpu().numpy()
+            for world in (1, 2, 3):
+                epoch += 1
+                frame[:] = -1.0
+                for rank in range(world):
+                    ctx.render_tiles_host(W, H, rank, world, spp, depth, 17, 2, alias, alias + flags_off + 4 * rank, epoch)
+                ctx.host_wait(address + flags_off, world, epoch)
+                assert (flags[:world] == epoch).all()
+                assert np.array_equal(frame, want), (spp, depth, world)
+        torch.cuda.synchronize()
+    finally:
+        ctx.host_unregister(address)
+        del frame, flags, buf
+        mm.close()

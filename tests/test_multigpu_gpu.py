@@ -59,6 +59,16 @@ def _worker(rank, world, port, out_dir):
                 np.save(os.path.join(out_dir, f"{name}_{mode}_seq.npy"), torch.stack(kept).cpu().numpy())
             dist.barrier()
             r.close()
+            if mode == "peer":                                      # frames assembled in shared HOST memory, every GPU pushing its own tiles
+                hosts = []
+                for k in range(5):
+                    hf = r.render_host(W, H, spp, depth, seed=5, sample_offset=k * spp)
+                    if rank == 0:
+                        hosts.append(hf.copy())
+                torch.cuda.synchronize()
+                if rank == 0:
+                    np.save(os.path.join(out_dir, f"{name}_host_seq.npy"), np.stack(hosts))
+                dist.barrier()
             if mode == "peer":                                      # a closed renderer starts afresh (frames, sync words, counters)
                 frame = r.render(W, H, spp, depth, seed=5)
                 torch.cuda.synchronize()
@@ -87,6 +97,7 @@ def test_all_partition_modes_match_single_gpu(tmp_path):
             assert np.array_equal(np.load(tmp_path / f"{name}_{mode}.npy"), full), (name, mode)   # bit-identical
             assert np.array_equal(np.load(tmp_path / f"{name}_{mode}_seq.npy"), seq), (name, mode)
         assert np.array_equal(np.load(tmp_path / f"{name}_reopened.npy"), full), name
+        assert np.array_equal(np.load(tmp_path / f"{name}_host_seq.npy"), seq[:5]), name
         for mode in ("samples", "peer_samples", "peer_samples+nccl"):
             np.testing.assert_allclose(np.load(tmp_path / f"{name}_{mode}.npy"), full, atol=3e-6)  # re-associated sum
             np.testing.assert_allclose(np.load(tmp_path / f"{name}_{mode}_seq.npy"), seq, atol=3e-6)
