@@ -482,3 +482,40 @@ def test_shared_host_frame_assembled_by_ranks(ctx):
         ctx.host_unregister(address)
         del frame, flags, buf
         mm.close()
+
+
+def test_banded_host_frames_and_staged_upload(ctx):
+    """(a) Host-buffer frames other than camera-ray frames go out as bands of tile rows, each copied while the next renders
+    (rt_render_host into page-locked memory, frames >= 4 MB): the tiny-scene route (the reference host's render(W,H,8,4)
+    on its default scene, after the library has timed its two kernel candidates) and the wavefront route.  (b) A scene
+    edit large enough for several staging chunks (300k triangles = 10.8 MB through the 4 MB page-locked ring): pixels
+    of the refitted tree == oracle on the edited scene."""
+    import torch
+    W, H = 1280, 992
+    pinned = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+    for make, spp, depth in [(scenes.default_scene, 8, 4), (lambda: scenes.random_triangles(20_000, seed=4), 2, 3)]:
+        s = make()
+        ctx.set_scene(s)
+        ctx.set_camera_array(s.camera.as_array(W / H))
+        for rep in range(4):                                     # the first two calls of a tiny scene time the candidates
+            dev = ctx.render(W, H, spp, depth, seed=3, sample_offset=rep).cpu().numpy()
+            pinned.zero_()
+            ctx.render_host(W, H, spp, depth, seed=3, sample_offset=rep, out=pinned.numpy())
+            assert np.array_equal(pinned.numpy(), dev), (s.name, rep)
+        pageable = ctx.render_host(W, H, spp, depth, seed=3, sample_offset=3)
+        assert np.array_equal(pageable, dev)
+    s = scenes.random_triangles(300_000, seed=41)
+    W, H = 256, 160
+    cam = s.camera.as_array(W / H)
+    ctx.set_scene(s)
+    ctx.set_camera_array(cam)
+    ctx.trace_primary(W, H)
+    m = _moved(s, 9, share=0.2, amount=0.4)
+    ctx.update_geometry(_prims(m))
+    prim, t = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
+    o = _oracle(m, cam)
+    op, ot, _ = o.trace_primary(W, H)
+    assert np.array_equal(prim, op) and np.array_equal(t, ot)
+    ctx.build_bvh(0)                                             # the host copy kept by the staged upload feeds a rebuild
+    prim2, t2 = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
+    assert np.array_equal(prim2, op) and np.array_equal(t2, ot)
