@@ -46,6 +46,11 @@ struct rt_ctx {
     int bvh_depth = 0;
     int64_t n_nodes = 0;                 // node records of the current tree (host vector `nodes` may be a stale mirror)
     float root_extent = 0.0f;            // max |coordinate| of the root box
+    int treelet_levels = 0;              // option "treelet": levels of the tree the packet kernel stages in shared memory (0: none)
+    float4* d_treelet = nullptr;         // 2^levels - 1 sibling pairs, heap order (k_build_treelet); rebuilt when the tree changes
+    int treelet_pairs = 0;
+    bool treelet_valid = false;
+    int leaf_size = 4;                   // option "leaf_size": primitives per leaf of builder 0 (4 = the reference's rule)
     int builder = 0;                     // option "builder": what set_scene -> render builds with (0 host median split, 1 device LBVH)
     rt_bvh_node* d_nodes_abi = nullptr;  // device-built tree in ABI layout, until the host mirror is asked for (rt_get_bvh)
     bool host_bvh_stale = false;
@@ -152,7 +157,7 @@ int cuda_fail(rt_ctx* c, const char* what, cudaError_t e) {
 void free_device_scene(rt_ctx* c) {
     cudaFree(c->d_nodes); cudaFree(c->d_prims); cudaFree(c->d_cam_prims); cudaFree(c->d_nodes_abi); c->d_nodes_abi = nullptr; cudaFree(c->d_slot_prim); cudaFree(c->d_mats);
     c->d_nodes = c->d_prims = c->d_cam_prims = c->d_mats = nullptr; c->d_slot_prim = nullptr;
-    c->device_valid = false; c->cam_table_ok = false;
+    c->device_valid = false; c->cam_table_ok = false; c->treelet_valid = false;
 }
 
 // Camera basis exactly as Camera::get_ray builds it (old/raytracer_core copy.h:160-184): forward
@@ -183,11 +188,13 @@ int ensure_bvh(rt_ctx* ctx);
 
 // RAII around every group of launches that uses context-owned scratch on `stream`: on entry, if the previous such group
 // ran on another stream, make `stream` wait for it; on exit, record the completion event the next group may have to wait on.
+int ensure_treelet(rt_ctx* ctx, cudaStream_t stream);
 struct ScratchOrder {
     rt_ctx* c; cudaStream_t st;
     ScratchOrder(rt_ctx* ctx, void* stream) : c(ctx), st((cudaStream_t)stream) {
         if (!c->scratch_ev) cudaEventCreateWithFlags(&c->scratch_ev, cudaEventDisableTiming);
         if (c->scratch_pending && c->scratch_stream != st) cudaStreamWaitEvent(st, c->scratch_ev, 0);
+        ensure_treelet(c, st);                                 // the staged top treelet follows the tree (option "treelet")
     }
     ~ScratchOrder() {
         if (c->scratch_ev && cudaEventRecord(c->scratch_ev, st) == cudaSuccess) { c->scratch_stream = st; c->scratch_pending = true; }
@@ -311,8 +318,22 @@ int ensure_bvh(rt_ctx* ctx) {
     return rt_build_bvh(ctx, ctx->builder);
 }
 
+// (Re)build the staged treelet for the current tree when option "treelet" asks for one.
+int ensure_treelet(rt_ctx* ctx, cudaStream_t stream) {
+    if (ctx->treelet_levels <= 0 || ctx->n_nodes <= 2 || !ctx->d_nodes) { ctx->treelet_pairs = 0; return 0; }
+    if (ctx->treelet_valid) return 0;
+    const int pairs = (1 << ctx->treelet_levels) - 1;
+    cudaFree(ctx->d_treelet); ctx->d_treelet = nullptr;
+    CK(cudaMalloc(&ctx->d_treelet, (size_t)pairs * 64));
+    CK(launch_build_treelet(ctx->d_nodes, pairs, ctx->d_treelet, stream));
+    ctx->treelet_pairs = pairs; ctx->treelet_valid = true;
+    return 0;
+}
+
 SceneView scene_view(const rt_ctx* c) {
     SceneView v;
+    v.treelet = (c->treelet_levels > 0 && c->treelet_valid && c->treelet_pairs > 0) ? c->d_treelet : nullptr;
+    v.treelet_two_t = v.treelet ? 2 * c->treelet_pairs : 0;
     v.nodes = c->d_nodes; v.prims = c->d_prims; v.cam_prims = c->d_cam_prims; v.slot_prim = c->d_slot_prim; v.mats = c->d_mats;
     v.n_prims = (int)c->n; v.n_nodes = (int)c->n_nodes; v.n_mats = c->m;
     v.sane_extent = 0;
@@ -524,6 +545,7 @@ void rt_destroy(rt_ctx* ctx) {
         cudaDeviceSynchronize();
         free_device_scene(ctx);
         free_wave(ctx);
+        cudaFree(ctx->d_treelet);
         cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick); cudaFree(ctx->d_edit); cudaFree(ctx->d_display); cudaFree(ctx->d_planes);
         cudaFree(ctx->d_band_cnt); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
         if (ctx->h_band_flags) cudaFreeHost(ctx->h_band_flags);
@@ -611,6 +633,7 @@ int rt_update_geometry(rt_ctx* ctx, const float* h_prims, int64_t n) {
     CK(bvh_area(ctx->d_nodes, (int)ctx->n_nodes, d_area, ctx->sm_count, nullptr));
     ctx->launches += 5;
     ctx->refits += 1;
+    ctx->treelet_valid = false;
     double area = 0.0;
     CK(cudaMemcpy(&area, d_area, sizeof(double), cudaMemcpyDeviceToHost));            // synchronises
     ctx->area_pct = ctx->built_area > 0.0 ? (int64_t)(100.0 * area / ctx->built_area) : 100;
@@ -724,7 +747,7 @@ int rt_build_bvh(rt_ctx* ctx, int builder) {
     PrimBoxes boxes;
     if (ctx->is_tri) triangle_boxes(ctx->prim_data.data(), ctx->n, boxes);
     else sphere_boxes(ctx->prim_data.data(), ctx->n, boxes);
-    build_median_split(boxes, ctx->n, ctx->nodes, ctx->prim_index);
+    build_median_split(boxes, ctx->n, ctx->nodes, ctx->prim_index, ctx->leaf_size);
     const char* msg;
     ctx->bvh_depth = validate_bvh(ctx->nodes.data(), (int64_t)ctx->nodes.size(), ctx->n, &msg);
     if (ctx->bvh_depth < 0) return fail(ctx, msg);
@@ -1380,6 +1403,8 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "overlap") { if (value < 0 || value > 2) return fail(ctx, "overlap must be 0 (render, then copy), 1 (region flags + DMA copies) or 2 (tile push)"); ctx->overlap = (int)value; }
     else if (k == "refit_limit") { if (value < 0 || value > 100000) return fail(ctx, "refit_limit must be 0 (never rebuild) or a percentage"); ctx->refit_limit = (int)value; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail(ctx, "builder must be 0 (reference median split, host) or 1 (LBVH, device)"); ctx->builder = (int)value; }
+    else if (k == "treelet") { if (value < 0 || value > 10) return fail(ctx, "treelet must be 0 (off) or 1..10 levels"); ctx->treelet_levels = (int)value; ctx->treelet_valid = false; }
+    else if (k == "leaf_size") { if (value < 1 || value > 4) return fail(ctx, "leaf_size must be in 1..4"); ctx->leaf_size = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
     else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);
     else if (k == "tiny_threads") { if (value != 128 && value != 256) return fail(ctx, "tiny_threads must be 128 or 256"); ctx->tiny_threads = (int)value; }
@@ -1406,6 +1431,8 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "n_prims") *value = ctx->n;
     else if (k == "n_nodes") *value = ctx->n_nodes;
     else if (k == "builder") *value = ctx->builder;
+    else if (k == "leaf_size") *value = ctx->leaf_size;
+    else if (k == "treelet") *value = ctx->treelet_levels;
     else if (k == "refit_limit") *value = ctx->refit_limit;
     else if (k == "refits") *value = ctx->refits;
     else if (k == "refit_rebuilds") *value = ctx->refit_rebuilds;

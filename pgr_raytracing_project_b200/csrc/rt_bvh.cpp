@@ -38,12 +38,13 @@ struct Builder {
     std::vector<int32_t>& idx;
     std::vector<rt_bvh_node>& nodes;
     std::map<int64_t, int64_t> memo;    // span -> node records used by the subtree's descendants
+    int64_t leaf = 4;                   // a range of at most this many primitives is a leaf (4: the reference's)
 
     // Number of node records (sibling pairs x 2) below a node spanning `span` primitives.  The
     // tree shape depends on span only (always split at span/2), which is what lets subtrees be
     // built in parallel at fixed, deterministic positions.
     int64_t records_below(int64_t span) {
-        if (span <= 4) return 0;
+        if (span <= leaf) return 0;
         auto it = memo.find(span);
         if (it != memo.end()) return it->second;
         int64_t l = span / 2;
@@ -52,7 +53,7 @@ struct Builder {
         return r;
     }
     int64_t records_below_ro(int64_t span) const {
-        if (span <= 4) return 0;
+        if (span <= leaf) return 0;
         return memo.at(span);
     }
 
@@ -66,7 +67,7 @@ struct Builder {
         }
         for (int c = 0; c < 3; ++c) { nd.bmin[c] = lo[c]; nd.bmax[c] = hi[c]; }
         int64_t span = end - start;
-        if (span <= 4) {
+        if (span <= leaf) {
             std::sort(idx.begin() + start, idx.begin() + end);
             nd.a = (int32_t)start; nd.b = (int32_t)span;
             return;
@@ -102,11 +103,12 @@ struct Builder {
 }  // namespace
 
 void build_median_split(const PrimBoxes& boxes, int64_t n, std::vector<rt_bvh_node>& nodes,
-                        std::vector<int32_t>& prim_index) {
+                        std::vector<int32_t>& prim_index, int leaf_size) {
     nodes.clear(); prim_index.clear();
     if (n == 0) return;
     prim_index.resize(n);
     Builder b{boxes, {}, prim_index, nodes, {}};
+    b.leaf = leaf_size < 1 ? 1 : (leaf_size > 4 ? 4 : leaf_size);
     b.ctr.resize(3 * n);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {

@@ -23,7 +23,7 @@ void triangle_boxes(const float* vertices9, int64_t n, PrimBoxes& out);
 // every box padded outward by 2^-16 * max |coordinate| of the root box.
 // Deterministic for any thread count.
 void build_median_split(const PrimBoxes& boxes, int64_t n, std::vector<rt_bvh_node>& nodes,
-                        std::vector<int32_t>& prim_index);
+                        std::vector<int32_t>& prim_index, int leaf_size = 4);   // leaf_size 1..4 (4 = the reference's rule)
 
 // Structural validation of a caller-supplied tree; returns max depth or -1 (msg filled).
 int validate_bvh(const rt_bvh_node* nodes, int64_t n_nodes, int64_t n_prims, const char** msg);

@@ -41,6 +41,8 @@ struct SceneView {
     const float4* __restrict__ cam_prims;  // triangles: camera-relative records for the current camera position (k_cam_tris)
     const int* __restrict__ slot_prim;     // slot -> primitive number (upload order)
     const float4* __restrict__ mats;       // 2 x float4 per material: albedo|metallic, roughness|emission
+    const float4* __restrict__ treelet;    // top levels of the tree as a heap of sibling pairs (k_build_treelet), or nullptr
+    int treelet_two_t;                     // 2 x pairs in the treelet = node records a CTA stages in shared memory (0: none)
     int n_prims;
     int n_nodes;
     int n_mats;
@@ -397,15 +399,16 @@ __device__ __forceinline__ void trav_pop(Trav& tv, const STACK& st) {
     tv.cur = kDone;
 }
 
+// two_t > 0: the kernel stages the top treelet in shared memory (see packet_walk): the root's children are node records 0, 1 of it
 template <bool STATS>
-__device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Trav& tv, Counters& cnt) {
+__device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Trav& tv, Counters& cnt, int two_t = 0) {
     tv.h.t = kTMax; tv.h.prim = -1; tv.h.slot = -1;
     tv.sp = 0; tv.cur = kDone;
     if (sc.n_nodes == 0) return;
     float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
     float tn;
     if (STATS) cnt.nodes += 1;
-    if (box_hit(lo, hi, r, kTMin, tv.h.t, tn)) tv.cur = __float_as_int(lo.w);
+    if (box_hit(lo, hi, r, kTMin, tv.h.t, tn)) tv.cur = two_t > 0 ? 0 : __float_as_int(lo.w);
 }
 
 // Runs the warp's traversals until fewer than `min_active` lanes still have work (warp-uniform call).
@@ -422,9 +425,9 @@ __device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Tr
 // CAM: 0 = no ray of this warp is a camera ray, 1 = all are, 2 = per lane (`cam`).
 constexpr int kNeedPop = (int)0x80000000;   // not a leaf code: would mean first slot 2^28 - 1, count 7
 
-template <bool TRI, bool STATS, int CAM, class STACK>
+template <bool TRI, bool STATS, int CAM, class STACK, bool TREELET = false>
 __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav& tv, const STACK& st, int min_active,
-                                         int leaf_vote, Counters& cnt, bool cam) {
+                                         int leaf_vote, Counters& cnt, bool cam, const float4* s_tree = nullptr, int two_t = 0) {
     for (;;) {
         if (tv.cur == kNeedPop) trav_pop(tv, st);
         const bool is_int = tv.cur >= 0, is_leaf = tv.cur < kDone;
@@ -442,15 +445,22 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
                 tv.cur = kNeedPop;
             }
         } else if (is_int) {
-            const float4* p = sc.nodes + 2 * (size_t)tv.cur;
             float4 l0, l1, r0, r1;
-            ldg_pair(p, l0, l1, r0, r1);
+            int lc, rc;
+            if (TREELET && tv.cur < two_t) {                  // per lane: top of the tree out of shared memory
+                const float4* p = s_tree + 2 * tv.cur;
+                l0 = p[0]; l1 = p[1]; r0 = p[2]; r1 = p[3];
+                lc = __float_as_int(l0.w); rc = __float_as_int(r0.w);
+            } else {
+                const float4* p = sc.nodes + 2 * (size_t)(TREELET ? tv.cur - two_t : tv.cur);
+                ldg_pair(p, l0, l1, r0, r1);
+                lc = __float_as_int(l0.w); rc = __float_as_int(r0.w);
+                if (TREELET) { lc = lc >= 0 ? lc + two_t : lc; rc = rc >= 0 ? rc + two_t : rc; }
+            }
             if (STATS) cnt.nodes += 2;
             float tl, tr;
             bool hl = box_hit(l0, l1, r, kTMin, tv.h.t, tl);
             bool hr = box_hit(r0, r1, r, kTMin, tv.h.t, tr);
-            int lc = __float_as_int(l0.w);
-            int rc = __float_as_int(r0.w);
             if (hl && hr) {
                 if (tr < tl) { int c = lc; lc = rc; rc = c; float tf = tl; tl = tr; tr = tf; }
                 st.put(tv.sp, rc, tr); ++tv.sp;
@@ -494,21 +504,34 @@ __device__ __forceinline__ bool box_hit_oct(const float4& lo, const float4& hi, 
     return n <= f;
 }
 
-template <bool TRI, bool STATS, int OCT>
+// TREELET (shared-memory staging of the top treelet, north_star): s_tree = the top levels of the tree staged in shared
+// memory by the CTA (SceneView::treelet: a heap of sibling pairs whose child codes are already in the kernel's code space:
+// code < two_t = node record of the staged heap, code >= two_t = global node record code - two_t).  The packet's node
+// address is warp-uniform, so the shared / global choice is a uniform branch.
+template <bool TRI, bool STATS, int OCT, bool TREELET = false>
 __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* __restrict__ cam_prims, const Ray& r, int lane,
-                                            uint2* __restrict__ stack, int cur, Hit& h, Counters& cnt, int& work) {
+                                            uint2* __restrict__ stack, int cur, Hit& h, Counters& cnt, int& work,
+                                            const float4* s_tree = nullptr, int two_t = 0) {
     int sp = 0;
     for (;;) {
         if (cur >= 0) {
-            const float4* p = sc.nodes + 2 * (size_t)cur;
             float4 l0, l1, r0, r1;
-            ldg_pair(p, l0, l1, r0, r1);
+            int lc, rc;
+            if (TREELET && cur < two_t) {
+                const float4* p = s_tree + 2 * cur;
+                l0 = p[0]; l1 = p[1]; r0 = p[2]; r1 = p[3];
+                lc = __float_as_int(l0.w); rc = __float_as_int(r0.w);
+            } else {
+                const float4* p = sc.nodes + 2 * (size_t)(TREELET ? cur - two_t : cur);
+                ldg_pair(p, l0, l1, r0, r1);
+                lc = __float_as_int(l0.w); rc = __float_as_int(r0.w);
+                if (TREELET) { lc = lc >= 0 ? lc + two_t : lc; rc = rc >= 0 ? rc + two_t : rc; }
+            }
             if (STATS && lane == 0) cnt.nodes += 2;
             work += 1;
             float tl, tr;
             const bool hl = box_hit_oct<OCT>(l0, l1, r, kTMin, h.t, tl);
             const bool hr = box_hit_oct<OCT>(r0, r1, r, kTMin, h.t, tr);
-            const int lc = __float_as_int(l0.w), rc = __float_as_int(r0.w);
             const unsigned bl = __ballot_sync(0xffffffffu, hl), br = __ballot_sync(0xffffffffu, hr);
             if (bl != 0u && br != 0u) {
                 // entry distances with +inf for a missed child: a lane votes "right first" iff tr' < tl'
@@ -543,10 +566,10 @@ __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* _
     }
 }
 
-template <bool TRI, bool STATS>
+template <bool TRI, bool STATS, bool TREELET = false>
 __device__ __forceinline__ void packet_intersect(const SceneView& sc, const float4* __restrict__ cam_prims, const Ray& r,
                                                  bool active, int lane, uint2* __restrict__ stack, Hit& h, Counters& cnt,
-                                                 int& work) {
+                                                 int& work, const float4* s_tree = nullptr) {
     h.t = active ? kTMax : 0.0f; h.prim = -1; h.slot = -1;
     if (sc.n_nodes == 0) return;
     const float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
@@ -554,23 +577,24 @@ __device__ __forceinline__ void packet_intersect(const SceneView& sc, const floa
     if (STATS && lane == 0) cnt.nodes += 1;
     const bool hit = box_hit(lo, hi, r, kTMin, h.t, tn);
     if (!__any_sync(0xffffffffu, hit)) return;
-    const int root = __float_as_int(lo.w);
+    const int two_t = TREELET ? sc.treelet_two_t : 0;
+    const int root = (TREELET && two_t > 0) ? 0 : __float_as_int(lo.w);          // staged heap: the root's children are pair 0
     // octant of the packet: sign bits of the direction; usable when all lanes agree, no component is
     // tiny (so 1/d, o/d and every slab product stay finite) and the scene is of sane extent
     const int oct = (r.dx < 0.0f ? 1 : 0) | (r.dy < 0.0f ? 2 : 0) | (r.dz < 0.0f ? 4 : 0);
     const bool tiny = !(fabsf(r.dx) >= 0x1p-60f && fabsf(r.dy) >= 0x1p-60f && fabsf(r.dz) >= 0x1p-60f);
     const int oct0 = __shfl_sync(0xffffffffu, oct, 0);
     const bool uniform = sc.sane_extent && __all_sync(0xffffffffu, oct == oct0 && !tiny);
-    if (!uniform) { packet_walk<TRI, STATS, 8>(sc, cam_prims, r, lane, stack, root, h, cnt, work); return; }
+    if (!uniform) { packet_walk<TRI, STATS, 8, TREELET>(sc, cam_prims, r, lane, stack, root, h, cnt, work, s_tree, two_t); return; }
     switch (oct0) {
-        case 0: packet_walk<TRI, STATS, 0>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
-        case 1: packet_walk<TRI, STATS, 1>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
-        case 2: packet_walk<TRI, STATS, 2>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
-        case 3: packet_walk<TRI, STATS, 3>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
-        case 4: packet_walk<TRI, STATS, 4>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
-        case 5: packet_walk<TRI, STATS, 5>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
-        case 6: packet_walk<TRI, STATS, 6>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
-        default: packet_walk<TRI, STATS, 7>(sc, cam_prims, r, lane, stack, root, h, cnt, work); break;
+        case 0: packet_walk<TRI, STATS, 0, TREELET>(sc, cam_prims, r, lane, stack, root, h, cnt, work, s_tree, two_t); break;
+        case 1: packet_walk<TRI, STATS, 1, TREELET>(sc, cam_prims, r, lane, stack, root, h, cnt, work, s_tree, two_t); break;
+        case 2: packet_walk<TRI, STATS, 2, TREELET>(sc, cam_prims, r, lane, stack, root, h, cnt, work, s_tree, two_t); break;
+        case 3: packet_walk<TRI, STATS, 3, TREELET>(sc, cam_prims, r, lane, stack, root, h, cnt, work, s_tree, two_t); break;
+        case 4: packet_walk<TRI, STATS, 4, TREELET>(sc, cam_prims, r, lane, stack, root, h, cnt, work, s_tree, two_t); break;
+        case 5: packet_walk<TRI, STATS, 5, TREELET>(sc, cam_prims, r, lane, stack, root, h, cnt, work, s_tree, two_t); break;
+        case 6: packet_walk<TRI, STATS, 6, TREELET>(sc, cam_prims, r, lane, stack, root, h, cnt, work, s_tree, two_t); break;
+        default: packet_walk<TRI, STATS, 7, TREELET>(sc, cam_prims, r, lane, stack, root, h, cnt, work, s_tree, two_t); break;
     }
 }
 

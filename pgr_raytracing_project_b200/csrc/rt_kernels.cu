@@ -314,6 +314,37 @@ __device__ __noinline__ void push_tile(const float* __restrict__ fb, float* __re
     }
 }
 
+// Top treelet for shared-memory staging: the first `levels` levels below the root as a HEAP of sibling pairs (pair 0 = the
+// root's children; the children of pair s's left / right node are pairs 2s + 1 / 2s + 2), 4 float4 per pair in the device
+// node format, child codes rewritten for a kernel that holds the heap in shared memory: code < two_t = node record of the
+// heap (2 x pair), code >= two_t = global node record code - two_t; leaf codes unchanged.  Pairs below a leaf stay empty.
+__global__ void __launch_bounds__(256)
+k_build_treelet(const float4* __restrict__ nodes, int n_pairs, float4* __restrict__ out) {
+    const int two_t = 2 * n_pairs;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_pairs; s += gridDim.x * blockDim.x) {
+        int g = __float_as_int(nodes[0].w);                    // the root's child pair (the root is internal: checked by the host)
+        const unsigned path = (unsigned)s + 1u;                // 1-based heap index: the bits below the leading one, top down
+        bool exists = true;
+        for (int bit = 30 - __clz(path); bit >= 0 && exists; --bit) {
+            const int side = (path >> bit) & 1u;
+            const int c = __float_as_int(nodes[2 * (size_t)(g + side)].w);
+            if (c < 0) exists = false; else g = c;
+        }
+        float4 rec[4] = {make_float4(0, 0, 0, __int_as_float(-1)), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, __int_as_float(-1)), make_float4(0, 0, 0, 0)};
+        if (exists) {
+            for (int k = 0; k < 4; ++k) rec[k] = nodes[2 * (size_t)g + k];
+            for (int side = 0; side < 2; ++side) {
+                const int c = __float_as_int(rec[2 * side].w);
+                if (c >= 0) {
+                    const int child = 2 * s + 1 + side;
+                    rec[2 * side].w = __int_as_float(child < n_pairs ? 2 * child : c + two_t);
+                }
+            }
+        }
+        for (int k = 0; k < 4; ++k) out[4 * (size_t)s + k] = rec[k];
+    }
+}
+
 // rt_render_tiles_host: one warp per tile of this launch's tile map (32x32 tiles): the tile's rows from the device frame
 // (L2) into the shared page-locked host frame, 384 contiguous bytes per row; the last warp to finish publishes `epoch`.
 __global__ void __launch_bounds__(256)
@@ -339,8 +370,11 @@ k_push_tiles(const __grid_constant__ TileMap tm, const float* __restrict__ fb, f
 // ptxas settles at 48 registers = 5 CTAs of 256 threads per SM, the measured optimum: forcing 40 / 32 registers (6 / 8
 // CTAs) spills and is 3 % / 18 % slower, and anything that pushes the kernel to 64 registers (4 CTAs) costs 4-5 % --
 // which is why the final pixel store here is the plain one and not warp_store_rgb
-template <bool TRI, bool STATS, bool AOV, bool ITEM>
-__global__ void __launch_bounds__(kPacketThreads)
+#ifndef PACKET_TREELET_MINB
+#define PACKET_TREELET_MINB 5
+#endif
+template <bool TRI, bool STATS, bool AOV, bool ITEM, bool TREELET = false>
+__global__ void __launch_bounds__(kPacketThreads, TREELET ? PACKET_TREELET_MINB : 1)
 k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_prims, const __grid_constant__ CameraBlock cam,
          const __grid_constant__ TileMap tm, int n_work, int spp, uint32_t k0, uint32_t k1, uint32_t sample_offset,
          int resolve, float* __restrict__ d_out, int32_t* __restrict__ d_prim, float* __restrict__ d_t,
@@ -355,8 +389,12 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
     // rank's tiles of a multi-GPU frame) still splits into enough items to balance.
     __shared__ uint2 s_stack[kPacketThreads / 32][kStackDepth];
     __shared__ unsigned s_word;
+    extern __shared__ float4 s_tree[];                         // TREELET: the top levels of the tree (SceneView::treelet)
     const int lane = threadIdx.x & 31;
     uint2* stack = s_stack[threadIdx.x >> 5];
+    if (TREELET) {
+        for (int k = threadIdx.x; k < 2 * sc.treelet_two_t; k += kPacketThreads) s_tree[k] = __ldg(sc.treelet + k);
+    }
     constexpr bool item_mode = ITEM && !AOV;
     const int n_items = item_mode ? n_work * plane_batch : n_work;
     const int n_chunks = (n_items + kChunk - 1) / kChunk;
@@ -387,7 +425,7 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
             }
             Ray r = camera_ray(cam, p.i, p.j, jx, jy, inv_w, inv_h);
             Hit h;
-            packet_intersect<TRI, STATS>(sc, cam_prims, r, p.active, lane, stack, h, cnt, work);
+            packet_intersect<TRI, STATS, TREELET>(sc, cam_prims, r, p.active, lane, stack, h, cnt, work, s_tree);
             if (STATS && p.active) { rays += 1; cnt.segments += 1; }
             if (AOV) {
                 if (p.active) { d_prim[p.out_index] = h.prim; d_t[p.out_index] = h.prim >= 0 ? h.t : 0.0f; }
@@ -565,6 +603,19 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
                                                   grid * (kPacketThreads / 32), cfg.sched.reorder_frames, cfg.band);
     }
     if (!item_mode) {
+        if (!STATS && sc.treelet != nullptr && sc.treelet_two_t > 0) {        // top treelet staged in shared memory (option "treelet")
+            const size_t smem = (size_t)sc.treelet_two_t * 32;
+            auto kern = k_packet<TRI, false, AOV, false, true>;
+            if (smem > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int per = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kPacketThreads, smem);
+            int g2 = cfg.sm_count * (per < 1 ? 1 : per);
+            if (g2 > need) g2 = need;
+            kern<<<g2, kPacketThreads, smem, cfg.stream>>>(
+                sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
+                d_prim, d_t, cfg.d_work_counter, nullptr, cfg.band, cfg.sched, cfg.d_block_times, nullptr, 1, 0);
+            return cudaGetLastError();
+        }
         k_packet<TRI, STATS, AOV, false><<<grid, kPacketThreads, 0, cfg.stream>>>(
             sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
             d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, nullptr, 1, 0);
@@ -727,6 +778,12 @@ cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, i
     double total = (double)n_old + (double)n_batch;
     float w_old = (float)((double)n_old / total), w_new = (float)((double)n_batch / total);
     k_accumulate<<<elementwise_grid(n), 256, 0, stream>>>(d_batch, d_accum, n, w_old, w_new, n_old == 0 ? 1 : 0);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_treelet(const float4* d_nodes, int n_pairs, float4* d_treelet, cudaStream_t stream) {
+    if (n_pairs <= 0) return cudaSuccess;
+    k_build_treelet<<<(n_pairs + 255) / 256, 256, 0, stream>>>(d_nodes, n_pairs, d_treelet);
     return cudaGetLastError();
 }
 

@@ -127,6 +127,8 @@ cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, i
                               cudaStream_t stream);
 // Barrier between the processes that share a frame (rt_frame_sync): words[0] = arrival counter, words[1] = error flag.
 cudaError_t launch_frame_sync(unsigned long long* words, unsigned long long target, cudaStream_t stream);
+// Top `n_pairs` sibling pairs of the tree (heap order) with child codes for shared-memory staging (rt_kernels.cu k_build_treelet).
+cudaError_t launch_build_treelet(const float4* d_nodes, int n_pairs, float4* d_treelet, cudaStream_t stream);
 // rt_render_tiles_host: this launch's 32x32 tiles of the device frame `fb` stored into the page-locked frame `host` (device
 // alias); the last warp to finish writes `epoch` to *flag (system scope).  cnt: one device word, zeroed here.
 cudaError_t launch_push_tiles(const TileMap& tm, const float* d_fb, float* d_host, unsigned int* d_flag, unsigned int epoch,

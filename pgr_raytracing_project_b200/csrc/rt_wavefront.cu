@@ -133,7 +133,7 @@ k_wf_packet0(const __grid_constant__ SceneView sc, const float4* __restrict__ ca
 }
 
 // CAM: the rays of this queue are camera rays (bounce 0 of variant 2: triangle test from the per-camera table)
-template <bool TRI, bool STATS, bool CAM>
+template <bool TRI, bool STATS, bool CAM, bool TREELET = false>
 __global__ void __launch_bounds__(kThreads)
 k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuffers wb, int bounce, int max_depth, int refill_below,
            int leaf_vote, unsigned long long* d_stats) {
@@ -144,6 +144,12 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
     const unsigned count = wb.counters[bounce];
     unsigned int* fetch = wb.counters + (max_depth + 1) + bounce;
     __shared__ uint2 s_stack[kWfSmemLevels][kThreads];
+    extern __shared__ float4 s_tree[];                         // TREELET: top levels of the tree (SceneView::treelet), option "treelet"
+    const int two_t = TREELET ? sc.treelet_two_t : 0;
+    if (TREELET) {
+        for (int k = threadIdx.x; k < 2 * two_t; k += kThreads) s_tree[k] = __ldg(sc.treelet + k);
+        __syncthreads();
+    }
     int stack_code[kStackDepth - kWfSmemLevels];
     float stack_tn[kStackDepth - kWfSmemLevels];
     const HybridStack<kWfSmemLevels, kThreads> stack{&s_stack[0][threadIdx.x], stack_code, stack_tn};
@@ -171,7 +177,7 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
                     q = (int)idx;
                     float4 o = __ldg(ray_o + idx), d = __ldg(ray_d + idx);
                     r = make_ray(o.x, o.y, o.z, d.x, d.y, d.z);
-                    trav_begin<STATS>(sc, r, tv, cnt);
+                    trav_begin<STATS>(sc, r, tv, cnt, two_t);
                 }
             }
             if (base + (unsigned)n_need >= count) pool_empty = true;
@@ -182,7 +188,8 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
             continue;                               // root misses waiting to be published / more to fetch
         }
         int min_active = pool_empty ? 1 : (__popc(act) * refill_below) >> 5;
-        trav_run<TRI, STATS, CAM ? 1 : 0>(sc, r, tv, stack, min_active < 1 ? 1 : min_active, leaf_vote, cnt, CAM);
+        trav_run<TRI, STATS, CAM ? 1 : 0, HybridStack<kWfSmemLevels, kThreads>, TREELET>(sc, r, tv, stack, min_active < 1 ? 1 : min_active, leaf_vote,
+                                                                                          cnt, CAM, s_tree, two_t);
     }
     if (STATS) flush_stats(d_stats, 0, cnt);
 }
@@ -318,7 +325,14 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
             for (int b = 0; b < depth; ++b) {
                 if (b == 0 && !packet0)
                     k_wf_trace<TRI, STATS, true><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
-                else if (b > 0)
+                else if (b > 0 && !STATS && sc.treelet != nullptr && sc.treelet_two_t > 0) {      // option "treelet": top levels staged in shared memory
+                    const size_t smem = (size_t)sc.treelet_two_t * 32;
+                    auto kern = k_wf_trace<TRI, false, false, true>;
+                    if (smem > 30 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    int per = 0;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kThreads, smem);
+                    kern<<<cfg.sm_count * (per < 1 ? 1 : per), kThreads, smem, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, nullptr);
+                } else if (b > 0)
                     k_wf_trace<TRI, STATS, false><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
                 k_wf_shade<TRI, STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(sc, wa, wb, b, d_prim, d_t,
                                                                                                       cfg.d_stats);

@@ -53,6 +53,11 @@ def main():
     for combo in itertools.product(*[opts[n] for n in names]) if names else [()]:
         for n, v in zip(names, combo):
             ctx.set_option(n, v)
+            if n == "leaf_size":
+                torch.cuda.synchronize(); tb = time.time()
+                ctx.build_bvh(0)
+                torch.cuda.synchronize()
+                print(f"  leaf_size={v}: build_bvh(0) {(time.time() - tb) * 1e3:.1f} ms, nodes {ctx.get_option('n_nodes')}, depth {ctx.get_option('bvh_depth')}", flush=True)
             if n == "builder":
                 torch.cuda.synchronize(); tb = time.time()
                 ctx.build_bvh(v)
