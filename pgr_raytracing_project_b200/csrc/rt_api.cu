@@ -110,6 +110,10 @@ struct rt_ctx {
     CameraBlock chunk_cam;                   // camera the current order was built for
     int schedule = 1;                        // option "schedule"
     unsigned long long* d_block_times = nullptr;   // debug option "block_times" (device pointer supplied by the caller)
+    unsigned int* d_fold_cnt = nullptr;      // item mode, one batch: per-block sample counters (fold_block)
+    size_t fold_cap = 0;
+    int fold = 0;                            // option "fold": 1 = the packet kernel folds the sample planes itself; 0 (default, measured faster:
+                                             // 2.81 vs 2.86 ms at 8 spp, 0.694 vs 0.743 ms at 2 spp on C3) = separate k_plane_accumulate pass
     float4* d_planes = nullptr;              // item mode of the packet kernel: sample planes (grow-only)
     size_t planes_cap = 0;                   // in float4
     void* d_display = nullptr;               // rt_display_u8 scratch (tone-mapped copy, sorted copy, sort workspace)
@@ -397,7 +401,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
     cfg.variant = variant >= 0 ? variant : pick_kernel(c, max_depth);
     c->kernel_used = cfg.variant;
     cfg.d_cam_prims = c->d_cam_prims;
-    cfg.d_planes = nullptr; cfg.plane_batch = 0;
+    cfg.d_planes = nullptr; cfg.plane_batch = 0; cfg.d_fold_cnt = nullptr;
     cfg.cam_table_valid = 0;
     cfg.band = BandSignal{nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 1, 1};
     cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr, 0};
@@ -427,6 +431,16 @@ int attach_planes(rt_ctx* ctx, LaunchCfg& cfg, const TileMap& tm, int spp) {
         ctx->planes_cap = need;
     }
     cfg.d_planes = ctx->d_planes; cfg.plane_batch = (int)batch;
+    if (ctx->fold && batch >= spp) {                          // one batch: the kernel folds the planes itself
+        const size_t blocks = (size_t)(n_tasks / 32);
+        if (blocks > ctx->fold_cap) {
+            cudaDeviceSynchronize();
+            cudaFree(ctx->d_fold_cnt); ctx->d_fold_cnt = nullptr; ctx->fold_cap = 0;
+            CK(cudaMalloc(&ctx->d_fold_cnt, blocks * sizeof(unsigned int)));
+            ctx->fold_cap = blocks;
+        }
+        cfg.d_fold_cnt = ctx->d_fold_cnt;
+    }
     return 0;
 }
 
@@ -483,6 +497,7 @@ int render_launches(const rt_ctx* ctx, const LaunchCfg& cfg, int spp = 1) {
     const int table = (ctx->is_tri && !cfg.cam_table_valid) ? 1 : 0;
     if (cfg.variant != 3) return 1 + table;
     const int order = (cfg.sched.order && cfg.sched.reorder_frames > 0) ? 1 : 0;
+    if (cfg.d_planes && spp > 1 && cfg.d_fold_cnt) return 1 + table + order;
     if (cfg.d_planes && spp > 1) return 2 * ((spp + cfg.plane_batch - 1) / cfg.plane_batch) + table + order;
     return 1 + table + order;
 }
@@ -545,7 +560,7 @@ void rt_destroy(rt_ctx* ctx) {
         cudaDeviceSynchronize();
         free_device_scene(ctx);
         free_wave(ctx);
-        cudaFree(ctx->d_treelet);
+        cudaFree(ctx->d_treelet); cudaFree(ctx->d_fold_cnt);
         cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick); cudaFree(ctx->d_edit); cudaFree(ctx->d_display); cudaFree(ctx->d_planes);
         cudaFree(ctx->d_band_cnt); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
         if (ctx->h_band_flags) cudaFreeHost(ctx->h_band_flags);
@@ -1403,6 +1418,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "overlap") { if (value < 0 || value > 2) return fail(ctx, "overlap must be 0 (render, then copy), 1 (region flags + DMA copies) or 2 (tile push)"); ctx->overlap = (int)value; }
     else if (k == "refit_limit") { if (value < 0 || value > 100000) return fail(ctx, "refit_limit must be 0 (never rebuild) or a percentage"); ctx->refit_limit = (int)value; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail(ctx, "builder must be 0 (reference median split, host) or 1 (LBVH, device)"); ctx->builder = (int)value; }
+    else if (k == "fold") ctx->fold = value != 0;
     else if (k == "treelet") { if (value < 0 || value > 10) return fail(ctx, "treelet must be 0 (off) or 1..10 levels"); ctx->treelet_levels = (int)value; ctx->treelet_valid = false; }
     else if (k == "leaf_size") { if (value < 1 || value > 4) return fail(ctx, "leaf_size must be in 1..4"); ctx->leaf_size = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
@@ -1433,6 +1449,7 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "builder") *value = ctx->builder;
     else if (k == "leaf_size") *value = ctx->leaf_size;
     else if (k == "treelet") *value = ctx->treelet_levels;
+    else if (k == "fold") *value = ctx->fold;
     else if (k == "refit_limit") *value = ctx->refit_limit;
     else if (k == "refits") *value = ctx->refits;
     else if (k == "refit_rebuilds") *value = ctx->refit_rebuilds;

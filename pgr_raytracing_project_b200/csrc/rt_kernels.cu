@@ -367,6 +367,26 @@ k_push_tiles(const __grid_constant__ TileMap tm, const float* __restrict__ fb, f
     }
 }
 
+// Item mode, single batch: the warp that finishes the LAST sample of a block adds the block's sample planes in sample order
+// (the other samples' planes come from other SMs: read through L2), resolves and stores the pixels -- k_plane_accumulate
+// folded into the render kernel, so a multi-sample frame is one launch and its pixels leave (to a peer GPU's frame, over
+// NVLink) while the rest of the frame is still being traced.  Out of line: k_packet's register budget.
+__device__ __noinline__ void fold_block(const float4* __restrict__ planes, size_t plane_stride, int slot, int batch, int spp, int resolve,
+                                        float* __restrict__ o, bool active, int lane) {
+    float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+    if (active) {
+        for (int s = 0; s < batch; ++s) {
+            const float4 c = __ldcg(planes + (size_t)s * plane_stride + slot);
+            sr = __fadd_rn(sr, c.x); sg = __fadd_rn(sg, c.y); sb = __fadd_rn(sb, c.z);
+        }
+        if (resolve) {
+            const float inv_spp = __fdiv_rn(1.0f, (float)spp);
+            sr = resolve1(sr, inv_spp); sg = resolve1(sg, inv_spp); sb = resolve1(sb, inv_spp);
+        }
+    }
+    warp_store_rgb(o, active, sr, sg, sb, lane);
+}
+
 // ptxas settles at 48 registers = 5 CTAs of 256 threads per SM, the measured optimum: forcing 40 / 32 registers (6 / 8
 // CTAs) spills and is 3 % / 18 % slower, and anything that pushes the kernel to 64 registers (4 CTAs) costs 4-5 % --
 // which is why the final pixel store here is the plain one and not warp_store_rgb
@@ -374,13 +394,13 @@ k_push_tiles(const __grid_constant__ TileMap tm, const float* __restrict__ fb, f
 #define PACKET_TREELET_MINB 5
 #endif
 template <bool TRI, bool STATS, bool AOV, bool ITEM, bool TREELET = false>
-__global__ void __launch_bounds__(kPacketThreads, TREELET ? PACKET_TREELET_MINB : 1)
+__global__ void __launch_bounds__(kPacketThreads, TREELET ? PACKET_TREELET_MINB : 0)
 k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_prims, const __grid_constant__ CameraBlock cam,
          const __grid_constant__ TileMap tm, int n_work, int spp, uint32_t k0, uint32_t k1, uint32_t sample_offset,
          int resolve, float* __restrict__ d_out, int32_t* __restrict__ d_prim, float* __restrict__ d_t,
          unsigned int* counter, unsigned long long* d_stats, const __grid_constant__ BandSignal band,
          const __grid_constant__ ChunkSchedule sched, unsigned long long* d_block_times, float4* __restrict__ planes,
-         int plane_batch, int plane_sample0) {
+         int plane_batch, int plane_sample0, unsigned int* fold_cnt) {
     // planes != nullptr: ITEM MODE for multi-sample frames -- the work item is (block, sample) instead of a block
     // with a sample loop inside: item = block * plane_batch + sb, sample plane_sample0 + sb, radiance written to
     // planes[sb][block * 32 + lane]; k_plane_accumulate then adds the planes in sample order (same bits as the
@@ -445,6 +465,16 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
             float* o = d_out + 3 * (size_t)p.out_index;
             if (resolve) { o[0] = resolve1(sr, inv_spp); o[1] = resolve1(sg, inv_spp); o[2] = resolve1(sb, inv_spp); }
             else { o[0] = sr; o[1] = sg; o[2] = sb; }
+        }
+        if (item_mode && fold_cnt != nullptr) {              // single batch: the block's last sample folds the planes into the pixels
+            __threadfence();                                 // release: this sample's plane entries before the count
+            __syncwarp();
+            unsigned last = 0u;
+            if (lane == 0) last = atomicAdd(fold_cnt + w, 1u) + 1u == (unsigned)plane_batch ? 1u : 0u;
+            if (__shfl_sync(0xffffffffu, last, 0)) {
+                __threadfence();                             // acquire: the other samples' plane entries
+                fold_block(planes, (size_t)n_work * 32, w * 32 + lane, plane_batch, spp, resolve, d_out + 3 * (size_t)p.out_index, p.active, lane);
+            }
         }
         if (sched.order != nullptr && lane == 0) {
             atomicAdd(sched.cost_sum + item / kChunk, (unsigned)work);
@@ -613,16 +643,24 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
             if (g2 > need) g2 = need;
             kern<<<g2, kPacketThreads, smem, cfg.stream>>>(
                 sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
-                d_prim, d_t, cfg.d_work_counter, nullptr, cfg.band, cfg.sched, cfg.d_block_times, nullptr, 1, 0);
+                d_prim, d_t, cfg.d_work_counter, nullptr, cfg.band, cfg.sched, cfg.d_block_times, nullptr, 1, 0, nullptr);
             return cudaGetLastError();
         }
         k_packet<TRI, STATS, AOV, false><<<grid, kPacketThreads, 0, cfg.stream>>>(
             sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
-            d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, nullptr, 1, 0);
+            d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, nullptr, 1, 0, nullptr);
         return cudaGetLastError();
     }
     // multi-sample frame: (block, sample) items, batches of <= plane_batch samples (the schedule is attached by the
     // caller only when one batch covers all samples)
+    if (batch_all >= spp && cfg.d_fold_cnt != nullptr) {           // one batch: planes folded by the kernel itself (fold_block)
+        cudaError_t e = cudaMemsetAsync(cfg.d_fold_cnt, 0, (size_t)n_work * sizeof(unsigned int), cfg.stream);
+        if (e != cudaSuccess) return e;
+        k_packet<TRI, STATS, false, true><<<grid, kPacketThreads, 0, cfg.stream>>>(
+            sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
+            d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, cfg.d_planes, spp, 0, cfg.d_fold_cnt);
+        return cudaGetLastError();
+    }
     for (int s0 = 0; s0 < spp; s0 += batch_all) {
         const int batch = spp - s0 < batch_all ? spp - s0 : batch_all;
         if (s0 > 0) {
@@ -631,7 +669,7 @@ cudaError_t launch_packet(const SceneView& sc, const CameraBlock& cam, const Til
         }
         k_packet<TRI, STATS, false, true><<<grid, kPacketThreads, 0, cfg.stream>>>(
             sc, cfg.d_cam_prims, cam, tm, n_work, spp, (uint32_t)seed, (uint32_t)(seed >> 32), sample_offset, resolve, d_out,
-            d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, cfg.d_planes, batch, s0);
+            d_prim, d_t, cfg.d_work_counter, cfg.d_stats, cfg.band, cfg.sched, cfg.d_block_times, cfg.d_planes, batch, s0, nullptr);
         const int n_tasks = n_work * 32;
         int ag = (n_tasks + 255) / 256, acap = cfg.sm_count * 8;
         k_plane_accumulate<<<ag > acap ? acap : ag, 256, 0, cfg.stream>>>(tm, n_tasks, batch, s0, spp, resolve, s0 + batch >= spp ? 1 : 0,

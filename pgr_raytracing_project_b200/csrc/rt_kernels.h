@@ -84,6 +84,7 @@ struct LaunchCfg {
     ChunkSchedule sched;                     // order == nullptr: raster order, no cost recording
     float4* d_planes;                        // item mode of k_packet (multi-sample frames): sample planes, plane_batch x tasks
     int plane_batch;                         // samples per batch the planes buffer holds for this tile map (0: loop mode)
+    unsigned int* d_fold_cnt;                // item mode, one batch: per-block sample counters (zeroed by the launcher); nullptr: k_plane_accumulate pass
     unsigned long long* d_block_times;       // debug (instrumented k_packet only): [2 * work item] = globaltimer start, end; or nullptr
     int tiny_threads;                        // k_tiny: threads per CTA (256 or 128)
     int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes

@@ -1,4 +1,8 @@
-M="l1tex__t_bytes.sum,lts__t_bytes.sum,l1tex__throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,smsp__inst_executed_op_shared_ld.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"
-for L in 0 6; do
-SPP=4 DEPTH=4 SWEEP="treelet=$L" timeout 600 ncu --set full --metrics $M --clock-control none -f -k regex:'k_wf_trace|k_wf_packet0' -s 4 -c 2 -o gpurun_out/r02h_treelet$L python tools/exp_bounce.py > gpurun_out/r02h_ncu$L.log 2>&1; echo rc=$?
-done
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edits_and_edge_cases.py -x -q -k "packet or auto or shared_host or two_streams" 2>&1 | tail -3
+timeout 300 python tools/tune.py c3s8 fold=1,0,1 2>&1 | grep -v scene
+timeout 300 python tools/tune.py c3s2 fold=1,0,1 2>&1 | grep -v scene
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/r02i_bench_n2.json 2> gpurun_out/r02i_bench_n2.err; echo "bench n2 rc=$?"
+python -c "
+import json; d=json.load(open('gpurun_out/r02i_bench_n2.json'))
+for k in ['value','ms_per_step','ms_per_step_stats','frame_matches_1gpu','host_frame_matches_1gpu','e2e','gpu_launches']: print(k, d[k])
+"
