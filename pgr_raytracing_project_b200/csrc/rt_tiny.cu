@@ -252,6 +252,84 @@ k_tiny(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
     }
 }
 
+// Lock-step form (option "tiny_mode" 1): one pixel per thread, samples and bounces in lock step inside the warp, no
+// compaction, no barriers, path state in registers -- k_render's structure with the scene in shared memory and the
+// two-pass brute-force closest hit.  Dead paths idle until the warp's last path of the sample ends (about 77 % of the
+// lanes busy on the Cornell box, against ~90 % after compaction), but warps never wait for each other.
+template <bool TRI, bool STATS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_tiny_lockstep(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock cam, const __grid_constant__ TinyArgs a,
+                float* __restrict__ d_out, unsigned int* counter, unsigned long long* d_stats) {
+    __shared__ float4 s_prims[kTinyMaxPrims * (TRI ? kTriStride : 1)];
+    __shared__ float4 s_cam[TRI ? kTinyMaxPrims * 3 : 1];
+    __shared__ int s_slot_prim[kTinyMaxPrims];
+    __shared__ float4 s_mats[kTinyMaxMats * 2];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = a.n;
+    for (int k = tid; k < n * (TRI ? kTriStride : 1); k += THREADS) s_prims[k] = __ldg(sc.prims + k);
+    for (int k = tid; k < n; k += THREADS) s_slot_prim[k] = TRI ? k : __ldg(sc.slot_prim + k);
+    for (int k = tid; k < a.m * 2; k += THREADS) s_mats[k] = __ldg(sc.mats + k);
+    __syncthreads();
+    if (TRI) {
+        for (int k = tid; k < n; k += THREADS)
+            cam_tri_record(s_prims[3 * k], s_prims[3 * k + 1], s_prims[3 * k + 2], cam.px, cam.py, cam.pz, s_cam[3 * k], s_cam[3 * k + 1],
+                           s_cam[3 * k + 2]);
+    }
+    __syncthreads();
+    SceneView ss = sc;
+    ss.prims = s_prims; ss.mats = s_mats; ss.slot_prim = s_slot_prim;
+    const double inv_w = __ddiv_rn(1.0, (double)a.tm.width), inv_h = __ddiv_rn(1.0, (double)a.tm.height);
+    const float inv_spp = __fdiv_rn(1.0f, (float)a.spp);
+    unsigned long long st_rays = 0, st_seg = 0;
+    for (;;) {
+        const int w = next_work(counter, lane);
+        if (w >= a.n_work) break;
+        const PixelWork p = decode_work(a.tm, w, lane);
+        const uint32_t pixel = (uint32_t)(p.j * a.tm.width + p.i);
+        float sum_r = 0.0f, sum_g = 0.0f, sum_b = 0.0f;
+        for (int s = 0; s < a.spp; ++s) {
+            const uint32_t sample = a.sample_offset + (uint32_t)s;
+            float cr = 0.0f, cg = 0.0f, cb = 0.0f, tr = 1.0f, tg = 1.0f, tb = 1.0f;
+            bool alive = p.active;
+            Ray r;
+            uint4 ctl = make_uint4(0u, 0u, 0u, 0u);
+            if (alive) {
+                ctl = philox4x32_10(pixel, sample, 0u, 0u, a.k0, a.k1);
+                r = camera_ray(cam, p.i, p.j, u01(ctl.x), u01(ctl.y), inv_w, inv_h);
+                if (STATS) st_rays += 1;
+            }
+            for (int b = 0; b < a.max_depth; ++b) {
+                if (!__any_sync(0xffffffffu, alive)) break;
+                if (alive) {
+                    Hit h;
+                    if (b == 0) tiny_closest<TRI, true>(s_prims, s_cam, s_slot_prim, n, r, h);
+                    else tiny_closest<TRI, false>(s_prims, s_cam, s_slot_prim, n, r, h);
+                    if (STATS) st_seg += 1;
+                    alive = false;
+                    if (h.prim < 0) {
+                        cr = __fmaf_rn(tr, sc.bg_r, cr); cg = __fmaf_rn(tg, sc.bg_g, cg); cb = __fmaf_rn(tb, sc.bg_b, cb);
+                    } else {
+                        const float4* mp = s_mats + 2 * material_row<TRI, true>(ss, h);
+                        const float4 m0 = mp[0], m1 = mp[1];
+                        cr = __fmaf_rn(tr, m1.y, cr); cg = __fmaf_rn(tg, m1.z, cg); cb = __fmaf_rn(tb, m1.w, cb);
+                        if (b + 1 < a.max_depth) {
+                            if (b > 0) ctl = philox4x32_10(pixel, sample, (uint32_t)b, 0u, a.k0, a.k1);
+                            alive = scatter<TRI, true>(ss, h, r, a.integrator, b, a.max_depth, ctl, m0, m1, pixel, sample, a.k0, a.k1, tr, tg, tb);
+                        }
+                    }
+                }
+            }
+            sum_r = __fadd_rn(sum_r, cr); sum_g = __fadd_rn(sum_g, cg); sum_b = __fadd_rn(sum_b, cb);
+        }
+        if (a.resolve) { sum_r = resolve1(sum_r, inv_spp); sum_g = resolve1(sum_g, inv_spp); sum_b = resolve1(sum_b, inv_spp); }
+        warp_store_rgb(d_out + 3 * (size_t)p.out_index, p.active, sum_r, sum_g, sum_b, lane);
+    }
+    if (STATS) {
+        Counters c = {0, (unsigned long long)n * st_seg, st_seg};
+        flush_stats(d_stats, st_rays, c);
+    }
+}
+
 }  // namespace
 
 bool tiny_eligible(const SceneView& sc, int n_mats, int max_depth) {
@@ -274,6 +352,21 @@ cudaError_t launch_tiny(const SceneView& sc, bool is_tri, int n_mats, const Came
     if (e != cudaSuccess) return e;
     const int n_items = (a.n_work + a.pb - 1) / a.pb;
     const bool st = cfg.d_stats != nullptr;
+    if (cfg.tiny_mode == 1) {
+#define LAUNCH_LS(T, S)                                                                                      \
+    {                                                                                                        \
+        int per_sm = 0;                                                                                      \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tiny_lockstep<T, S, 128, 8>, 128, 0);       \
+        int grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);                                                 \
+        const int need = (a.n_work + 3) / 4;                                                                 \
+        if (grid > need) grid = need;                                                                        \
+        k_tiny_lockstep<T, S, 128, 8><<<grid, 128, 0, cfg.stream>>>(sc, cam, a, d_out, cfg.d_work_counter, cfg.d_stats); \
+    }
+        if (is_tri) { if (st) LAUNCH_LS(true, true) else LAUNCH_LS(true, false) }
+        else { if (st) LAUNCH_LS(false, true) else LAUNCH_LS(false, false) }
+#undef LAUNCH_LS
+        return cudaGetLastError();
+    }
 #define LAUNCH(T, S, TH, MB)                                                                                 \
     {                                                                                                        \
         int per_sm = 0;                                                                                      \

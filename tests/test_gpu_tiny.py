@@ -34,12 +34,14 @@ SCENES = {
 }
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["cta_wavefront", "lockstep"])
 @pytest.mark.parametrize("name", list(SCENES))
 @pytest.mark.parametrize("W,H,spp,depth", [
     (96, 64, 1, 4), (97, 63, 2, 3), (50, 35, 3, 4), (64, 36, 4, 2), (41, 29, 5, 5), (64, 64, 8, 4), (33, 31, 11, 8),
     (40, 24, 64, 4), (64, 48, 7, 1), (8, 4, 1, 1), (1, 1, 9, 4),
 ])
-def test_tiny_kernel_bit_exact_vs_oracle(ctx, name, W, H, spp, depth):
+def test_tiny_kernel_bit_exact_vs_oracle(ctx, name, W, H, spp, depth, mode):
+    ctx.set_option("tiny_mode", mode)        # 0: CTA-local wavefront with compaction; 1: one pixel per thread, lock step
     s = SCENES[name]()
     cam = s.camera.as_array(W / H)
     ctx.set_scene(s)
@@ -61,6 +63,7 @@ def test_tiny_kernel_bit_exact_vs_oracle(ctx, name, W, H, spp, depth):
         oraw, _ = o.render(W, H, spp, depth, seed=0x5EED0002, sample_offset=3, integrator=integrator, resolve=False)
         assert np.array_equal(raw, oraw)
     ctx.set_option("integrator", 0)
+    ctx.set_option("tiny_mode", 0)
 
 
 @pytest.mark.parametrize("name", ["default9", "cornell36"])
