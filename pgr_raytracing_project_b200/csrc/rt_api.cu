@@ -71,7 +71,7 @@ struct rt_ctx {
     double fov = 45.0, aspect = 1.333;
 
     // options
-    int integrator = 0, stats = 0, kernel = -1, refill = 8, leaf_vote = 8, tiny_threads = 256, tiny_mode = 0;
+    int integrator = 0, stats = 0, kernel = -1, refill = 8, leaf_vote = 8, tiny_threads = 256, tiny_mode = 0, wf_rays_per_lane = 0;
     int kernel_used = -1;                    // variant picked by the most recent tracing launch
     // auto choice for multi-bounce renders of tiny scenes (<= 64 primitives): which of the lock-step megakernel
     // (open scenes, short paths: the reference's default scene) and the wavefront (closed scenes, long paths: a
@@ -406,7 +406,7 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
     cfg.band = BandSignal{nullptr, nullptr, nullptr, nullptr, 0, 0, 1, 1, 1};
     cfg.sched = ChunkSchedule{nullptr, nullptr, nullptr, 0};
     cfg.d_block_times = c->stats ? c->d_block_times : nullptr;
-    cfg.tiny_threads = c->tiny_threads; cfg.tiny_mode = c->tiny_mode;
+    cfg.tiny_threads = c->tiny_threads; cfg.tiny_mode = c->tiny_mode; cfg.wf_rays_per_lane = c->wf_rays_per_lane;
     cfg.refill_below = c->refill;
     cfg.leaf_vote = c->leaf_vote;
     return cfg;
@@ -1423,6 +1423,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "leaf_size") { if (value < 1 || value > 4) return fail(ctx, "leaf_size must be in 1..4"); ctx->leaf_size = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
     else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);
+    else if (k == "wf_rays_per_lane") { if (value < 0 || value > 1024) return fail(ctx, "wf_rays_per_lane must be in 0..1024"); ctx->wf_rays_per_lane = (int)value; }
     else if (k == "tiny_mode") { if (value != 0 && value != 1) return fail(ctx, "tiny_mode must be 0 (CTA-local wavefront) or 1 (lock step)"); ctx->tiny_mode = (int)value; }
     else if (k == "tiny_threads") { if (value != 128 && value != 256) return fail(ctx, "tiny_threads must be 128 or 256"); ctx->tiny_threads = (int)value; }
     else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
@@ -1441,6 +1442,7 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "refill") *value = ctx->refill;
     else if (k == "tiny_threads") *value = ctx->tiny_threads;
     else if (k == "tiny_mode") *value = ctx->tiny_mode;
+    else if (k == "wf_rays_per_lane") *value = ctx->wf_rays_per_lane;
     else if (k == "overlap") *value = ctx->overlap;
     else if (k == "schedule") *value = ctx->schedule;
     else if (k == "leaf_vote") *value = ctx->leaf_vote;

@@ -86,6 +86,7 @@ struct LaunchCfg {
     int plane_batch;                         // samples per batch the planes buffer holds for this tile map (0: loop mode)
     unsigned int* d_fold_cnt;                // item mode, one batch: per-block sample counters (zeroed by the launcher); nullptr: k_plane_accumulate pass
     unsigned long long* d_block_times;       // debug (instrumented k_packet only): [2 * work item] = globaltimer start, end; or nullptr
+    int wf_rays_per_lane;                    // k_wf_trace: CTAs beyond queue / (128 x this) leave at once (0: the whole grid works)
     int tiny_threads;                        // k_tiny: threads per CTA (256 or 128)
     int tiny_mode;                           // 0 = CTA-local wavefront with compaction (k_tiny), 1 = lock step per warp (k_tiny_lockstep)
     int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes

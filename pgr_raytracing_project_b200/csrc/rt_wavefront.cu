@@ -98,35 +98,39 @@ k_wf_packet0(const __grid_constant__ SceneView sc, const float4* __restrict__ ca
     __shared__ unsigned s_word;
     const int lane = threadIdx.x & 31;
     uint2* stack = s_stack[threadIdx.x >> 5];
+    // work item = (block, sample of the wave's batch), the samples of a block being consecutive items: the 8 warps of a CTA
+    // trace one block's samples side by side (shared L1 lines), and a wave of few blocks and many samples -- one rank's
+    // tiles of a multi-GPU frame -- still splits into enough items to balance (a block with its sample loop inside left
+    // 1.4 items per resident warp at 8 ranks)
     const int n_blocks = wa.n_tasks_wave >> 5, block0 = wa.task0 >> 5;
-    const int n_chunks = (n_blocks + kChunk - 1) / kChunk;
+    const int n_items = n_blocks * wa.batch;
+    const int n_chunks = (n_items + kChunk - 1) / kChunk;
     if (threadIdx.x == 0) s_word = take_chunk(chunk_counter, n_chunks, nullptr);
     __syncthreads();
     const double inv_w = __ddiv_rn(1.0, (double)wa.tm.width), inv_h = __ddiv_rn(1.0, (double)wa.tm.height);
     Counters cnt = {0, 0, 0};
     unsigned long long rays = 0;
     for (;;) {
-        const int wl = chunk_next_block(&s_word, chunk_counter, n_chunks, nullptr, lane);
-        if (wl < 0) break;
-        if (wl >= n_blocks) continue;
+        const int item = chunk_next_block(&s_word, chunk_counter, n_chunks, nullptr, lane);
+        if (item < 0) break;
+        if (item >= n_items) continue;
+        const int wl = item / wa.batch, sb = item - wl * wa.batch;
         PixelWork p = decode_work(wa.tm, block0 + wl, lane);
         const uint32_t pixel = (uint32_t)(p.j * wa.tm.width + p.i);
-        for (int sb = 0; sb < wa.batch; ++sb) {
-            uint4 ctl = philox4x32_10(pixel, wa.sample_offset + (uint32_t)(wa.sample0 + sb), 0u, 0u, wa.k0, wa.k1);
-            Ray r = camera_ray(cam, p.i, p.j, u01(ctl.x), u01(ctl.y), inv_w, inv_h);
-            Hit h;
-            int work = 0;
-            packet_intersect<TRI, STATS>(sc, cam_prims, r, p.active, lane, stack, h, cnt, work);
-            if (STATS && p.active) rays += 1;
-            const int slot = (wl * 32 + lane) * wa.batch + sb;
-            const unsigned q = warp_append(wb.counters, p.active, lane);
-            if (p.active) {
-                wb.ray_o[0][q] = make_float4(r.ox, r.oy, r.oz, __int_as_float(slot));
-                wb.ray_d[0][q] = make_float4(r.dx, r.dy, r.dz, 0.0f);
-                wb.hit[q] = make_float4(h.t, __int_as_float(h.prim), __int_as_float(h.slot), 0.0f);
-                wb.path_thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-                wb.path_rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            }
+        uint4 ctl = philox4x32_10(pixel, wa.sample_offset + (uint32_t)(wa.sample0 + sb), 0u, 0u, wa.k0, wa.k1);
+        Ray r = camera_ray(cam, p.i, p.j, u01(ctl.x), u01(ctl.y), inv_w, inv_h);
+        Hit h;
+        int work = 0;
+        packet_intersect<TRI, STATS>(sc, cam_prims, r, p.active, lane, stack, h, cnt, work);
+        if (STATS && p.active) rays += 1;
+        const int slot = (wl * 32 + lane) * wa.batch + sb;
+        const unsigned q = warp_append(wb.counters, p.active, lane);
+        if (p.active) {
+            wb.ray_o[0][q] = make_float4(r.ox, r.oy, r.oz, __int_as_float(slot));
+            wb.ray_d[0][q] = make_float4(r.dx, r.dy, r.dz, 0.0f);
+            wb.hit[q] = make_float4(h.t, __int_as_float(h.prim), __int_as_float(h.slot), 0.0f);
+            wb.path_thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            wb.path_rad[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
     }
     if (STATS) flush_stats(d_stats, rays, cnt);
@@ -136,12 +140,20 @@ k_wf_packet0(const __grid_constant__ SceneView sc, const float4* __restrict__ ca
 template <bool TRI, bool STATS, bool CAM, bool TREELET = false>
 __global__ void __launch_bounds__(kThreads)
 k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuffers wb, int bounce, int max_depth, int refill_below,
-           int leaf_vote, unsigned long long* d_stats) {
+           int leaf_vote, unsigned long long* d_stats, int rays_per_lane) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const float4* __restrict__ ray_o = wb.ray_o[bounce & 1];
     const float4* __restrict__ ray_d = wb.ray_d[bounce & 1];
     const unsigned count = wb.counters[bounce];
+    // Small queues (one rank's share of a multi-GPU frame, deep bounces): the grid is sized for the machine, not for the
+    // queue, and with one or two rays per lane the refill has nothing to even out -- the kernel then lasts as long as its
+    // unluckiest warp.  CTAs beyond what gives every lane `rays_per_lane` rays leave at once (never fewer than gridDim / 8).
+    if (rays_per_lane > 0) {
+        const unsigned want = (count + (unsigned)(kThreads * rays_per_lane) - 1u) / (unsigned)(kThreads * rays_per_lane);
+        const unsigned keep = want > gridDim.x / 8u ? want : gridDim.x / 8u;
+        if (blockIdx.x >= keep) return;
+    }
     unsigned int* fetch = wb.counters + (max_depth + 1) + bounce;
     __shared__ uint2 s_stack[kWfSmemLevels][kThreads];
     extern __shared__ float4 s_tree[];                         // TREELET: top levels of the tree (SceneView::treelet), option "treelet"
@@ -314,7 +326,7 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
             if (packet0) {
                 e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), st);
                 if (e != cudaSuccess) return e;
-                int need = ((nt >> 5) + kChunk - 1) / kChunk;
+                int need = ((nt >> 5) * batch + kChunk - 1) / kChunk;
                 k_wf_packet0<TRI, STATS><<<packet_grid < need ? packet_grid : need, kPacketThreads, 0, st>>>(
                     sc, cfg.d_cam_prims, cam, wa, wb, cfg.d_work_counter, cfg.d_stats);
             } else {
@@ -324,16 +336,16 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
             int depth = AOV ? 1 : max_depth;
             for (int b = 0; b < depth; ++b) {
                 if (b == 0 && !packet0)
-                    k_wf_trace<TRI, STATS, true><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
+                    k_wf_trace<TRI, STATS, true><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats, cfg.wf_rays_per_lane);
                 else if (b > 0 && !STATS && sc.treelet != nullptr && sc.treelet_two_t > 0) {      // option "treelet": top levels staged in shared memory
                     const size_t smem = (size_t)sc.treelet_two_t * 32;
                     auto kern = k_wf_trace<TRI, false, false, true>;
                     if (smem > 30 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                     int per = 0;
                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kThreads, smem);
-                    kern<<<cfg.sm_count * (per < 1 ? 1 : per), kThreads, smem, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, nullptr);
+                    kern<<<cfg.sm_count * (per < 1 ? 1 : per), kThreads, smem, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, nullptr, cfg.wf_rays_per_lane);
                 } else if (b > 0)
-                    k_wf_trace<TRI, STATS, false><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats);
+                    k_wf_trace<TRI, STATS, false><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats, cfg.wf_rays_per_lane);
                 k_wf_shade<TRI, STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(sc, wa, wb, b, d_prim, d_t,
                                                                                                       cfg.d_stats);
                 *n_launches += (packet0 && b == 0) ? 1 : 2;
