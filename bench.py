@@ -14,9 +14,12 @@ every GPU renders all samples of its 32x32 tiles and stores the resolved pixels 
 bit-identical to the 1-GPU frame.
 
 One JSON line on stdout (rank 0).  `value` is device-timed with the scene resident in HBM; `e2e`
-is the same frame through the C-ABI host-buffer call (rt_set_camera + rt_render_host: camera in,
-float32 frame out to pinned host memory) timed by the host clock; `roofline` rates the dominant
-kernel against the algorithmic bytes/ray; `cpu_baseline` is the oracle port on the host cores.
+is the same frame through the C-ABI host-buffer call (rt_set_camera + rt_render_host at N = 1,
+DistributedRenderer.render_host at N > 1: camera in, float32 frame out to pinned host memory) timed
+by the host clock; `roofline` rates the dominant kernel against its binding resource (instruction
+issue; the SURVEY 8(d) algorithmic-bytes figure is the sub-object `hbm_algorithmic`); `cpu_baseline`
+is the oracle port on the host cores, whose first frame also checks the GPU's; at N > 1 the timed
+frame is checked against the same frame rendered by one GPU (`frame_matches_1gpu`).
 `--impl reference` times the CPU implementation alone (see reference_arm()).
 """
 from __future__ import annotations
