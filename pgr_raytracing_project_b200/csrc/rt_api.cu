@@ -88,6 +88,10 @@ struct rt_ctx {
 
     WaveBuffers wave = {{nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr, 0};
     int wave_depth = 0;                      // counters sized for this max_depth
+    // two waves in flight (option "wf_streams" 2): second buffer set, two internal streams, fork / join / accumulate-order events
+    WaveBuffers wave2 = {{nullptr, nullptr}, {nullptr, nullptr}, nullptr, nullptr, nullptr, nullptr, 0};
+    int wf_streams = 2;
+    WavePipe pipe = {nullptr, {nullptr, nullptr}, nullptr, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
 
     float* d_fb = nullptr;                   // rt_render_host framebuffer
     size_t fb_floats = 0;
@@ -205,11 +209,40 @@ struct ScratchOrder {
     }
 };
 
+void free_wave_set(WaveBuffers& w) {
+    for (int k = 0; k < 2; ++k) { cudaFree(w.ray_o[k]); cudaFree(w.ray_d[k]); w.ray_o[k] = w.ray_d[k] = nullptr; }
+    cudaFree(w.hit); cudaFree(w.path_thr); cudaFree(w.path_rad); cudaFree(w.counters);
+    w.hit = w.path_thr = w.path_rad = nullptr; w.counters = nullptr;
+    w.capacity = 0;
+}
 void free_wave(rt_ctx* c) {
-    for (int k = 0; k < 2; ++k) { cudaFree(c->wave.ray_o[k]); cudaFree(c->wave.ray_d[k]); c->wave.ray_o[k] = c->wave.ray_d[k] = nullptr; }
-    cudaFree(c->wave.hit); cudaFree(c->wave.path_thr); cudaFree(c->wave.path_rad); cudaFree(c->wave.counters);
-    c->wave.hit = c->wave.path_thr = c->wave.path_rad = nullptr; c->wave.counters = nullptr;
-    c->wave.capacity = 0; c->wave_depth = 0;
+    free_wave_set(c->wave); free_wave_set(c->wave2);
+    c->wave_depth = 0;
+}
+int alloc_wave_set(rt_ctx* ctx, WaveBuffers& w, int64_t cap, int depth) {
+    size_t b = (size_t)cap * sizeof(float4);
+    for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&w.ray_o[k], b)); CK(cudaMalloc(&w.ray_d[k], b)); }
+    CK(cudaMalloc(&w.hit, b)); CK(cudaMalloc(&w.path_thr, b)); CK(cudaMalloc(&w.path_rad, b));
+    CK(cudaMalloc(&w.counters, sizeof(unsigned int) * 2 * (depth + 2)));
+    w.capacity = (int)cap;
+    return 0;
+}
+// the pipe of a wavefront launch: nullptr members = one wave at a time
+const WavePipe* wave_pipe(rt_ctx* ctx) {
+    WavePipe& p = ctx->pipe;
+    p.wave2 = nullptr;
+    if (ctx->wf_streams < 2 || ctx->wave2.capacity == 0) return &p;
+    if (!p.streams[0]) {
+        for (int k = 0; k < 2; ++k) {
+            if (cudaStreamCreateWithFlags(&p.streams[k], cudaStreamNonBlocking) != cudaSuccess) return &p;
+            cudaEventCreateWithFlags(&p.join[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&p.acc[k], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming);
+    }
+    p.counters[0] = ctx->d_work_counter; p.counters[1] = ctx->d_work_counter + 4;
+    p.wave2 = &ctx->wave2;
+    return &p;
 }
 
 // Wavefront buffers: grow-only, sized for min(paths of the call, 8 Mi) paths per wave.
@@ -218,16 +251,15 @@ int ensure_wave(rt_ctx* ctx, int64_t n_tasks, int spp, int max_depth) {
     const int64_t kCap = (int64_t)8 << 20;
     if (want > kCap) want = n_tasks > kCap ? kCap : (kCap / n_tasks) * n_tasks;
     if (want < 1024) want = 1024;
-    if (want <= ctx->wave.capacity && max_depth <= ctx->wave_depth) return 0;
+    const bool want2 = ctx->wf_streams >= 2;
+    if (want <= ctx->wave.capacity && max_depth <= ctx->wave_depth && (!want2 || ctx->wave2.capacity == ctx->wave.capacity)) return 0;
     int64_t cap = want > ctx->wave.capacity ? want : ctx->wave.capacity;
     int depth = max_depth > ctx->wave_depth ? max_depth : ctx->wave_depth;
     cudaDeviceSynchronize();
     free_wave(ctx);
-    size_t b = (size_t)cap * sizeof(float4);
-    for (int k = 0; k < 2; ++k) { CK(cudaMalloc(&ctx->wave.ray_o[k], b)); CK(cudaMalloc(&ctx->wave.ray_d[k], b)); }
-    CK(cudaMalloc(&ctx->wave.hit, b)); CK(cudaMalloc(&ctx->wave.path_thr, b)); CK(cudaMalloc(&ctx->wave.path_rad, b));
-    CK(cudaMalloc(&ctx->wave.counters, sizeof(unsigned int) * 2 * (depth + 2)));
-    ctx->wave.capacity = (int)cap; ctx->wave_depth = depth;
+    if (int rc = alloc_wave_set(ctx, ctx->wave, cap, depth)) return rc;
+    if (want2) { if (int rc = alloc_wave_set(ctx, ctx->wave2, cap, depth)) return rc; }
+    ctx->wave_depth = depth;
     return 0;
 }
 
@@ -570,6 +602,12 @@ void rt_destroy(rt_ctx* ctx) {
         for (auto& e : ctx->band_ev) if (e) cudaEventDestroy(e);
         if (ctx->tune_ev0) { cudaEventDestroy(ctx->tune_ev0); cudaEventDestroy(ctx->tune_ev1); }
         if (ctx->scratch_ev) cudaEventDestroy(ctx->scratch_ev);
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->pipe.streams[k]) cudaStreamDestroy(ctx->pipe.streams[k]);
+            if (ctx->pipe.join[k]) cudaEventDestroy(ctx->pipe.join[k]);
+            if (ctx->pipe.acc[k]) cudaEventDestroy(ctx->pipe.acc[k]);
+        }
+        if (ctx->pipe.fork) cudaEventDestroy(ctx->pipe.fork);
         for (int k = 0; k < 2; ++k) { if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]); if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]); }
         if (ctx->stage_stream) cudaStreamDestroy(ctx->stage_stream);
     }
@@ -863,7 +901,7 @@ int rt_trace_primary(rt_ctx* ctx, int width, int height, int32_t* d_prim, float*
         int nl = 0;
         LaunchCfg wcfg = launch_cfg(ctx, stream);
         claim_cam_table(ctx, wcfg, cam);
-        CK(launch_wavefront(scene_view(ctx), ctx->is_tri, true, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t, wcfg, ctx->wave, &nl));
+        CK(launch_wavefront(scene_view(ctx), ctx->is_tri, true, cam, tm, 1, 1, 0, 0, 0, 0, nullptr, d_prim, d_t, wcfg, ctx->wave, &nl, wave_pipe(ctx)));
         ctx->launches += nl;
         return 0;
     }
@@ -946,7 +984,7 @@ static int render_tiles(rt_ctx* ctx, int width, int height, int tile_w, int tile
         LaunchCfg wcfg = launch_cfg(ctx, stream, max_depth);
         claim_cam_table(ctx, wcfg, cam);
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
-                            resolve, d_out, nullptr, nullptr, wcfg, ctx->wave, &nl));
+                            resolve, d_out, nullptr, nullptr, wcfg, ctx->wave, &nl, wave_pipe(ctx)));
         ctx->launches += nl;
         return 0;
     }
@@ -1112,7 +1150,7 @@ static int render_frame(rt_ctx* ctx, int width, int height, int spp, int max_dep
         LaunchCfg wcfg = launch_cfg(ctx, stream, max_depth, variant);
         claim_cam_table(ctx, wcfg, cam);
         CK(launch_wavefront(scene_view(ctx), ctx->is_tri, false, cam, tm, spp, max_depth, ctx->integrator, seed, sample_offset,
-                            resolve, d_out, nullptr, nullptr, wcfg, ctx->wave, &nl));
+                            resolve, d_out, nullptr, nullptr, wcfg, ctx->wave, &nl, wave_pipe(ctx)));
         ctx->launches += nl;
         if (tuned) tune_end(ctx, (cudaStream_t)stream);
         return 0;
@@ -1423,6 +1461,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "leaf_size") { if (value < 1 || value > 4) return fail(ctx, "leaf_size must be in 1..4"); ctx->leaf_size = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
     else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);
+    else if (k == "wf_streams") { if (value != 1 && value != 2) return fail(ctx, "wf_streams must be 1 (one wave at a time) or 2 (two waves in flight)"); ctx->wf_streams = (int)value; }
     else if (k == "wf_rays_per_lane") { if (value < 0 || value > 1024) return fail(ctx, "wf_rays_per_lane must be in 0..1024"); ctx->wf_rays_per_lane = (int)value; }
     else if (k == "tiny_mode") { if (value != 0 && value != 1) return fail(ctx, "tiny_mode must be 0 (CTA-local wavefront) or 1 (lock step)"); ctx->tiny_mode = (int)value; }
     else if (k == "tiny_threads") { if (value != 128 && value != 256) return fail(ctx, "tiny_threads must be 128 or 256"); ctx->tiny_threads = (int)value; }
@@ -1443,6 +1482,7 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "tiny_threads") *value = ctx->tiny_threads;
     else if (k == "tiny_mode") *value = ctx->tiny_mode;
     else if (k == "wf_rays_per_lane") *value = ctx->wf_rays_per_lane;
+    else if (k == "wf_streams") *value = ctx->wf_streams;
     else if (k == "overlap") *value = ctx->overlap;
     else if (k == "schedule") *value = ctx->schedule;
     else if (k == "leaf_vote") *value = ctx->leaf_vote;

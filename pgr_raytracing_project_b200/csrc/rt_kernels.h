@@ -104,10 +104,18 @@ struct WaveBuffers {
     int capacity;            // paths per wave
 };
 
+// Two waves in flight (LaunchCfg::wave2 != nullptr): the frame's waves alternate between two buffer sets on two internal streams,
+// so that one wave's kernel tails (the last, longest rays of a persistent trace kernel) overlap the other wave's kernels.
+struct WavePipe {
+    const WaveBuffers* wave2;        // second buffer set, or nullptr: one wave at a time on cfg.stream
+    cudaStream_t streams[2];
+    cudaEvent_t fork, join[2], acc[2];
+    unsigned int* counters[2];       // chunk counters of k_wf_packet0, one per set
+};
 cudaError_t launch_wavefront(const SceneView& sc, bool is_tri, bool aov, const CameraBlock& cam, const TileMap& tm,
                              int spp, int max_depth, int integrator, uint64_t seed, uint32_t sample_offset, int resolve,
                              float* d_out, int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb,
-                             int* n_launches);
+                             int* n_launches, const WavePipe* pipe = nullptr);
 // tiny scenes (rt_tiny.cu): the whole scene staged in shared memory, brute-force closest hit, CTA-local wavefront
 bool tiny_eligible(const SceneView& sc, int n_mats, int max_depth);
 cudaError_t launch_tiny(const SceneView& sc, bool is_tri, int n_mats, const CameraBlock& cam, const TileMap& tm, int spp, int max_depth,

@@ -292,7 +292,7 @@ int grid_for(int64_t n, int threads, int sm_count, int per_sm) {
 template <bool TRI, bool STATS, bool AOV>
 cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const TileMap& tm, int spp, int max_depth,
                           int integrator, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out,
-                          int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb, int* n_launches) {
+                          int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb0, int* n_launches, const WavePipe* pipe) {
     const bool packet0 = !AOV && cfg.variant == 4;             // bounce 0 by camera-ray packets
     if (TRI && !cfg.cam_table_valid) {                         // bounce 0 (camera rays) reads the camera-relative table
         cudaError_t e = launch_cam_tris(sc, cam, cfg);
@@ -306,15 +306,29 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
         packet_grid = cfg.sm_count * (per_sm < 1 ? 1 : per_sm);
     }
     const int n_tasks = work_items(tm) * 32;
-    const int cap = wb.capacity;
-    const int chunk = n_tasks < cap ? n_tasks : (cap & ~31);
+    const int cap = wb0.capacity;
+    const bool two = pipe != nullptr && pipe->wave2 != nullptr && !AOV && (int64_t)n_tasks * spp >= 65536;
+    int chunk = n_tasks < cap ? n_tasks : (cap & ~31);
+    if (two && spp == 1 && chunk == n_tasks) chunk = (((n_tasks + 1) / 2) + 31) & ~31;         // at least two waves: split the pixels ...
     const int trace_grid = resident_grid(k_wf_trace<TRI, STATS, false>, cfg.sm_count);
-    cudaStream_t st = cfg.stream;
+    if (two) {                                                 // fork: both internal streams start after what precedes on cfg.stream
+        cudaError_t e = cudaEventRecord(pipe->fork, cfg.stream);
+        if (e != cudaSuccess) return e;
+        cudaStreamWaitEvent(pipe->streams[0], pipe->fork, 0);
+        cudaStreamWaitEvent(pipe->streams[1], pipe->fork, 0);
+    }
+    int wave = 0;
+    bool acc_pending[2] = {false, false};
     for (int task0 = 0; task0 < n_tasks; task0 += chunk) {
         int nt = n_tasks - task0 < chunk ? n_tasks - task0 : chunk;
         int batch_max = cap / nt;
         if (batch_max < 1) batch_max = 1;
-        for (int s0 = 0; s0 < spp;) {
+        if (two && spp >= 2 && batch_max > (spp + 1) / 2) batch_max = (spp + 1) / 2;             // ... or the samples
+        for (int s0 = 0; s0 < spp; ++wave) {
+            const int set = two ? (wave & 1) : 0;
+            const WaveBuffers& wb = set ? *pipe->wave2 : wb0;
+            cudaStream_t st = two ? pipe->streams[set] : cfg.stream;
+            unsigned int* chunk_counter = two ? pipe->counters[set] : cfg.d_work_counter;
             int batch = spp - s0 < batch_max ? spp - s0 : batch_max;
             WaveArgs wa;
             wa.tm = tm; wa.task0 = task0; wa.n_tasks_wave = nt; wa.sample0 = s0; wa.batch = batch;
@@ -324,11 +338,11 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
             cudaError_t e = cudaMemsetAsync(wb.counters, 0, sizeof(unsigned int) * 2 * (max_depth + 2), st);
             if (e != cudaSuccess) return e;
             if (packet0) {
-                e = cudaMemsetAsync(cfg.d_work_counter, 0, sizeof(unsigned int), st);
+                e = cudaMemsetAsync(chunk_counter, 0, sizeof(unsigned int), st);
                 if (e != cudaSuccess) return e;
                 int need = ((nt >> 5) * batch + kChunk - 1) / kChunk;
                 k_wf_packet0<TRI, STATS><<<packet_grid < need ? packet_grid : need, kPacketThreads, 0, st>>>(
-                    sc, cfg.d_cam_prims, cam, wa, wb, cfg.d_work_counter, cfg.d_stats);
+                    sc, cfg.d_cam_prims, cam, wa, wb, chunk_counter, cfg.d_stats);
             } else {
                 k_wf_generate<STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(cam, wa, wb, cfg.d_stats);
             }
@@ -351,10 +365,19 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
                 *n_launches += (packet0 && b == 0) ? 1 : 2;
             }
             if (!AOV) {
+                // per-pixel sums are taken in SAMPLE ORDER: this wave's accumulate follows the previous wave's, whichever stream that ran on
+                if (two && acc_pending[set ^ 1]) cudaStreamWaitEvent(st, pipe->acc[set ^ 1], 0);
                 k_wf_accumulate<<<grid_for(nt, 256, cfg.sm_count, 8), 256, 0, st>>>(wa, wb, d_out);
                 *n_launches += 1;
+                if (two) { cudaEventRecord(pipe->acc[set], st); acc_pending[set] = true; }
             }
             s0 += batch;
+        }
+    }
+    if (two) {                                                 // join
+        for (int k = 0; k < 2; ++k) {
+            cudaEventRecord(pipe->join[k], pipe->streams[k]);
+            cudaStreamWaitEvent(cfg.stream, pipe->join[k], 0);
         }
     }
     return cudaGetLastError();
@@ -365,11 +388,11 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
 cudaError_t launch_wavefront(const SceneView& sc, bool is_tri, bool aov, const CameraBlock& cam, const TileMap& tm,
                              int spp, int max_depth, int integrator, uint64_t seed, uint32_t sample_offset, int resolve,
                              float* d_out, int32_t* d_prim, float* d_t, const LaunchCfg& cfg, const WaveBuffers& wb,
-                             int* n_launches) {
+                             int* n_launches, const WavePipe* pipe) {
     if (work_items(tm) == 0) return cudaSuccess;
     bool st = cfg.d_stats != nullptr;
 #define RUN(T, S, A) return run_wavefront<T, S, A>(sc, cam, tm, spp, max_depth, integrator, seed, sample_offset, resolve, \
-                                                    d_out, d_prim, d_t, cfg, wb, n_launches)
+                                                    d_out, d_prim, d_t, cfg, wb, n_launches, pipe)
     if (aov) {
         if (is_tri) { if (st) RUN(true, true, true); else RUN(true, false, true); }
         else { if (st) RUN(false, true, true); else RUN(false, false, true); }
