@@ -133,3 +133,83 @@ def test_world2_gloo_matches_single_process(tmp_path, mode):
         assert np.array_equal(frame, full)          # bit-identical to the 1-process frame
     else:
         np.testing.assert_allclose(frame, full, atol=2e-6)   # float re-association of the sample sum
+
+
+# ------------------------------------------------------------------ frames assembled in shared host memory (render_host)
+class _OracleCtx:
+    """Stands in for RenderContext in DistributedRenderer.render_host on a machine without a GPU: the same four calls
+    (host_register / render_tiles_host / host_wait / host_unregister), with the CPU oracle rendering the rank's
+    skew-dealt tiles and plain stores into the shared mapping instead of the GPU's -- so the PROTOCOL (the /dev/shm file
+    every process maps, the flag words, the two alternating buffers, the back-pressure on the producers) runs for real
+    between two processes."""
+
+    def __init__(self, oracle, delay=0.0):
+        import ctypes
+        self.o, self.delay, self.C = oracle, delay, ctypes
+
+    def host_register(self, address, nbytes):
+        return address                                   # "device alias" = the host address itself
+
+    def host_unregister(self, address):
+        pass
+
+    def render_tiles_host(self, W, H, rank, world, spp, depth, seed, sample_offset, d_frame, d_flag, epoch):
+        import time
+        C = self.C
+        frame = np.ctypeslib.as_array(C.cast(d_frame, C.POINTER(C.c_float)), shape=(H, W, 3))
+        plan = TilePlan(W, H, 32, 32, world)
+        for tile in skewed_tiles_of(plan, rank):
+            x0, y0, w, h = plan.tile_rect(tile)
+            img, _ = self.o.render(W, H, spp, depth, seed=seed, sample_offset=sample_offset, rect=(x0, y0, w, h))
+            frame[y0:y0 + h, x0:x0 + w] = img
+            time.sleep(self.delay)
+        C.cast(d_flag, C.POINTER(C.c_uint32))[0] = epoch
+
+    def host_wait(self, flags_address, n, epoch, timeout_s=60.0):
+        import time
+        C = self.C
+        flags = C.cast(flags_address, C.POINTER(C.c_uint32))
+        t0 = time.time()
+        while any(flags[k] != epoch for k in range(n)):
+            assert time.time() - t0 < timeout_s, "a rank did not deliver its tiles"
+            time.sleep(0.0005)
+
+
+def _host_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ.setdefault("OMP_NUM_THREADS", "2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as orc
+    from pgr_raytracing_project_b200 import scenes
+    from pgr_raytracing_project_b200.multigpu import DistributedRenderer
+    s = scenes.default_scene()
+    W, H, spp, depth, seed = 100, 70, 2, 2, 23
+    o = orc.OracleScene(s)
+    o.set_camera(s.camera.as_array(W / H))
+    # rank 1 is FAST and rank 0 slow: without the back-pressure rank 1 would overwrite a buffer rank 0 still reads
+    r = DistributedRenderer(_OracleCtx(o, delay=0.004 if rank == 0 else 0.0), rank, world, mode="peer")
+    got = []
+    for k in range(6):                                   # different consecutive frames, two alternating host buffers
+        frame = r.render_host(W, H, spp, depth, seed=seed, sample_offset=k * spp)
+        if rank == 0:
+            import time
+            time.sleep(0.01)                             # the consumer dawdles before it copies the frame out
+            got.append(frame.copy())
+    dist.barrier()
+    if rank == 0:
+        want = [o.render(W, H, spp, depth, seed=seed, sample_offset=k * spp)[0] for k in range(6)]
+        np.save(os.path.join(out_dir, "host_got.npy"), np.stack(got))
+        np.save(os.path.join(out_dir, "host_want.npy"), np.stack(want))
+        assert not [f for f in os.listdir("/dev/shm") if f.startswith("b200rt_%d_" % os.getpid())]    # the name is gone
+    r._host = {}                                         # (no CUDA context to synchronise in close())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world2_gloo_shared_host_frames(tmp_path):
+    mp.spawn(_host_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got, want = np.load(tmp_path / "host_got.npy"), np.load(tmp_path / "host_want.npy")
+    assert not np.array_equal(want[0], want[1])
+    assert np.array_equal(got, want)
