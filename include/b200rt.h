@@ -229,7 +229,13 @@ int rt_display_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
  * "overlap" = how rt_render_host moves a camera-ray frame (max_depth 1, 1 spp) to the host: 2 (default) = TILE
  * PUSH, the render kernel itself stores every finished 32x32 tile into h_out (needs page-locked, 16-byte aligned
  * h_out; otherwise mode 1 is used), 1 = finished regions are copied by the DMA engine while the kernel renders the
- * rest, 0 = render, then one copy. */
+ * rest, 0 = render, then one copy; other frames of >= 4 MB into page-locked memory go out as bands of tile rows, each copied while
+ * the next renders.  Read-only "host_path" says which way the last rt_render_host took (0 copy, 1 regions, 2 tile push, 3 bands).
+ * "kernel" 5 = tiny scenes (<= 64 primitives, max_depth <= 8): the whole scene staged in shared memory (rt_tiny.cu), "tiny_mode"
+ * 0 / 1 = its CTA-local wavefront / lock-step form, "tiny_threads" 128 / 256; "treelet" 0..10 = levels of the tree staged in shared
+ * memory by the packet / incoherent-ray kernels (0 = off, the measured optimum); "leaf_size" 1..4 = primitives per leaf of builder 0
+ * (4 = the reference's rule); "wf_streams" 1 / 2 = waves of a wavefront frame in flight (2: kernel tails overlap); "fold",
+ * "wf_rays_per_lane" = measured-and-dropped variants kept for A/B runs. */
 int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);
 int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value);
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);   /* synchronises the device */

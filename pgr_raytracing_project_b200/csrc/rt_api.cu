@@ -101,6 +101,8 @@ struct rt_ctx {
     unsigned int* d_band_cnt = nullptr;
     unsigned int* h_band_flags = nullptr;    // cudaHostAlloc mapped
     unsigned int* d_band_flags = nullptr;    // device alias of h_band_flags
+    int host_path = -1;                      // read-only option "host_path": how the last rt_render_host moved its frame:
+                                             // 0 render, then one copy; 1 region flags + DMA copies; 2 tile push; 3 bands (render / copy overlapped)
     int overlap = 2;                         // option "overlap": 0 render then copy, 1 region flags + DMA copies, 2 tile push
     unsigned int* d_tile_cnt = nullptr;      // tile push: one completion counter per 32x32 tile
     int tile_cnt_cap = 0;
@@ -1391,7 +1393,8 @@ int rt_render_host(rt_ctx* ctx, int width, int height, int spp, int max_depth, u
     if (ctx->overlap && pick_kernel(ctx, max_depth) == 3 && max_depth == 1 && spp == 1 && ctx->n > 0 && need >= ((size_t)1 << 18)) {
         CK(cudaStreamSynchronize(nullptr));               // order after earlier work of the legacy stream
         if (ctx->overlap >= 2)
-            if (float* alias = pushable_alias(h_out)) return render_host_push(ctx, width, height, spp, seed, sample_offset, alias);
+            if (float* alias = pushable_alias(h_out)) { ctx->host_path = 2; return render_host_push(ctx, width, height, spp, seed, sample_offset, alias); }
+        ctx->host_path = 1;
         return render_host_overlapped(ctx, width, height, spp, seed, sample_offset, h_out);
     }
     // frames of >= 4 MB into page-locked memory: bands, copy overlapped (tiny scenes first let rt_render time its two kernel
@@ -1399,8 +1402,10 @@ int rt_render_host(rt_ctx* ctx, int width, int height, int spp, int max_depth, u
     if (ctx->overlap && max_depth >= 1 && ctx->n > 0 && need * sizeof(float) >= ((size_t)4 << 20) && height >= 256 &&
         !(tunes(ctx, max_depth) && ctx->tune_state < 2) && is_page_locked(h_out)) {
         CK(cudaStreamSynchronize(nullptr));
+        ctx->host_path = 3;
         return render_host_banded(ctx, width, height, spp, max_depth, seed, sample_offset, h_out);
     }
+    ctx->host_path = 0;
     if (int rc = rt_render(ctx, width, height, spp, max_depth, seed, sample_offset, ctx->d_fb, nullptr)) return rc;
     CK(cudaMemcpy(h_out, ctx->d_fb, need * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
@@ -1484,6 +1489,7 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "wf_rays_per_lane") *value = ctx->wf_rays_per_lane;
     else if (k == "wf_streams") *value = ctx->wf_streams;
     else if (k == "overlap") *value = ctx->overlap;
+    else if (k == "host_path") *value = ctx->host_path;
     else if (k == "schedule") *value = ctx->schedule;
     else if (k == "leaf_vote") *value = ctx->leaf_vote;
     else if (k == "sm_count") *value = ctx->sm_count;

@@ -381,6 +381,13 @@ def test_render_host_matches_device_render(ctx, W, H):
             pinned.zero_()
             ctx.render_host(W, H, spp, depth, seed=77, sample_offset=3, out=pinned.numpy())
             assert np.array_equal(pinned.numpy(), dev), (depth, spp, overlap)
+            # the library says which way the frame went (read-only option "host_path"): 2 = tile push, 1 = region copies,
+            # 3 = bands, 0 = render then copy -- nothing falls back silently
+            path = ctx.get_option("host_path")
+            if ctx.get_option("kernel_used") == 3 and depth == 1 and spp == 1 and overlap and W * H * 3 >= (1 << 18):
+                assert path == (2 if overlap == 2 else 1), (path, overlap)
+            else:
+                assert path in (0, 3), path
         # a view into a larger page-locked buffer at an offset that is not 16-byte aligned: falls back to mode 1
         big = torch.empty(H * W * 3 + 8, dtype=torch.float32, pin_memory=True)
         view = big[1:1 + H * W * 3].view(H, W, 3)
