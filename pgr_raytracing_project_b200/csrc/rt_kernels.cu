@@ -518,6 +518,43 @@ __global__ void __launch_bounds__(256)
 k_plane_accumulate(const __grid_constant__ TileMap tm, int n_tasks, int batch, int sample0, int spp, int resolve, int last,
                    const float4* __restrict__ planes, float* __restrict__ d_out) {
     const float inv_spp = __fdiv_rn(1.0f, (float)spp);
+    if (tm.tile_w == 32 && tm.tile_h == 32 && !tm.compact && (tm.width & 3) == 0) {
+        // frame layout, 32x32 tiles: one warp per TILE ROW (lane = pixel of the row), the row's 96 floats staged in shared memory
+        // and stored as 24 x 16 bytes = 384 contiguous, 128-byte aligned bytes -- full lines instead of the 96-byte runs of an
+        // 8x4 block's rows.  That matters when the frame is another GPU's (peer stores over NVLink: a rank's second pass took
+        // 30 us longer than the display rank's with the block-wise stores).
+        __shared__ float s_row[8][96];
+        const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+        const int n_rows = tm.n_local_tiles * 32, n_warps = gridDim.x * 8;
+        for (int row = blockIdx.x * 8 + wib; row < n_rows; row += n_warps) {
+            const int kt = row >> 5, y = row & 31;
+            const int tile = tm.first_tile + kt * tm.tile_stride;
+            const int ty = tile / tm.tiles_x;
+            int tx = tile - ty * tm.tiles_x;
+            if (tm.skew) tx = (tx + tm.skew * ty) % tm.tiles_x;
+            const int i = tx * 32 + lane, j = ty * 32 + y;
+            if (j >= tm.height) continue;                                // warp-uniform
+            const bool active = i < tm.width;
+            const int k = ((kt * 32 + (y >> 2) * 4 + (lane >> 3)) << 5) + ((y & 3) << 3) + (lane & 7);
+            float* o = d_out + 3 * ((size_t)j * tm.width + i);
+            float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+            if (active) {
+                if (sample0 > 0) { sr = o[0]; sg = o[1]; sb = o[2]; }
+                for (int s = 0; s < batch; ++s) {
+                    const float4 c = planes[(size_t)s * n_tasks + k];
+                    sr = __fadd_rn(sr, c.x); sg = __fadd_rn(sg, c.y); sb = __fadd_rn(sb, c.z);
+                }
+                if (last && resolve) { sr = resolve1(sr, inv_spp); sg = resolve1(sg, inv_spp); sb = resolve1(sb, inv_spp); }
+            }
+            if (tx * 32 + 32 <= tm.width) {                             // whole row inside the frame (warp-uniform)
+                s_row[wib][3 * lane] = sr; s_row[wib][3 * lane + 1] = sg; s_row[wib][3 * lane + 2] = sb;
+                __syncwarp();
+                if (lane < 24) reinterpret_cast<float4*>(o - 3 * lane)[lane] = reinterpret_cast<const float4*>(s_row[wib])[lane];
+                __syncwarp();
+            } else if (active) { o[0] = sr; o[1] = sg; o[2] = sb; }
+        }
+        return;
+    }
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_tasks; k += gridDim.x * blockDim.x) {   // n_tasks % 32 == 0
         PixelWork p = decode_work(tm, k >> 5, k & 31);
         float* o = d_out + 3 * (size_t)p.out_index;
