@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200rt.h"
@@ -1125,11 +1126,15 @@ int rt_render_tiles_host(rt_ctx* ctx, int width, int height, int rank, int world
 int rt_host_wait(const volatile uint32_t* h_flags, int n, uint32_t epoch, double timeout_s) {
     if (!h_flags || n <= 0) return 1;
     const auto t0 = std::chrono::steady_clock::now();
-    for (;;) {
+    for (unsigned spins = 0;; ++spins) {
         bool all = true;
         for (int k = 0; k < n; ++k) all = all && h_flags[k] == epoch;
         if (all) { std::atomic_thread_fence(std::memory_order_acquire); return 0; }
-        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) return 2;
+        if ((spins & 1023u) == 1023u) {                       // frames take fractions of a millisecond: spin, but look at the clock now and then,
+            const double waited = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (waited > timeout_s) return 2;
+            if (waited > 0.002) std::this_thread::yield();     // and stop hogging the core once the wait is not a frame's any more
+        }
     }
 }
 
