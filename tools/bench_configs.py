@@ -103,7 +103,7 @@ def main():
         out = {"config": name, "workload": workload, "n_gpus": world, "width": W, "height": H, "spp": spp, "max_depth": depth,
                "ms_per_frame": ms, "ms_per_frame_min": ms_min, "Msamples_per_s": W * H * spp / ms / 1e3,
                "Msegments_per_s": segments / ms / 1e3, "segments_per_frame": segments,
-               "kernel": {0: "k_path", 1: "k_render", 2: "wavefront", 3: "k_packet", 4: "wavefront+packet0"}.get(kernel, "?"),
+               "kernel": {0: "k_path", 1: "k_render", 2: "wavefront", 3: "k_packet", 4: "wavefront+packet0", 5: "k_tiny"}.get(kernel, "?"),
                "partition": "single GPU" if world == 1 else "peer tiles (32x32, skew-dealt), frame on rank 0"}
         out.update(extra or {})
         emit(out)
