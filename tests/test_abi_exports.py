@@ -56,3 +56,31 @@ def test_headline_kernel_register_budget():
     m = re.search(r"Compiling entry function '[^']*k_packetILb1ELb0ELb0ELb0E[^']*'.*?Used (\d+) registers", log, flags=re.S)
     assert m, "k_packet<TRI, !STATS, !AOV, !ITEM> not found in the ptxas log"
     assert int(m.group(1)) <= 48, f"k_packet uses {m.group(1)} registers"
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/b200rt.h is the boundary a C host binds: it must compile as C11 (gcc, not g++), and a C program that takes
+    the address of every declared entry point must link against libb200rt.so and run (rt_create fails loudly without a GPU)."""
+    import subprocess
+    build.build()
+    names = _declared()
+    src = tmp_path / "abi_user.c"
+    body = "\n".join(f"    table[n++] = (void*)&{n};" for n in names)
+    src.write_text(
+        '#include <stdio.h>\n#include "b200rt.h"\n'
+        "int main(void) {\n"
+        f"    void* table[{len(names) + 1}]; int n = 0;\n{body}\n"
+        "    if (rt_abi_version() != B200RT_ABI_VERSION) return 2;\n"
+        "    rt_ctx* ctx = NULL;\n"
+        "    int rc = rt_create(0, &ctx);\n"
+        '    for (int k = 0; k < n; ++k) if (!table[k]) return 3;\n'
+        '    printf("%d symbols, rt_create rc=%d: %s\\n", n, rc, rc ? rt_last_error(NULL) : "ok");\n'
+        "    if (!rc) rt_destroy(ctx);\n"
+        "    return 0;\n}\n")
+    exe = tmp_path / "abi_user"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lb200rt", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert f"{len(names)} symbols" in out.stdout
