@@ -331,11 +331,18 @@ int ensure_device(rt_ctx* ctx) {
         if (ctx->is_tri) CK(cudaMalloc(&ctx->d_cam_prims, (size_t)n * 3 * sizeof(float4)));
         CK(cudaMalloc(&ctx->d_slot_prim, (size_t)n * sizeof(int)));
         CK(cudaMemcpy(ctx->d_slot_prim, ctx->prim_index.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
-        // device node = bmin | code, bmax | 0: code >= 0 child-pair index, code <= -2 leaf ~((first << 3) | count)
-        std::vector<rt_bvh_node> dn(ctx->nodes);
-        for (auto& nd : dn) { nd.a = nd.b == 0 ? nd.a : ~((nd.a << 3) | nd.b); nd.b = 0; }
-        CK(cudaMalloc(&ctx->d_nodes, (size_t)n_nodes * sizeof(rt_bvh_node)));
-        CK(cudaMemcpy(ctx->d_nodes, dn.data(), (size_t)n_nodes * sizeof(rt_bvh_node), cudaMemcpyHostToDevice));
+        // device nodes: box + code (code >= 0 child-pair index, code <= -2 leaf ~((first << 3) | count)), sibling pairs interleaved
+        // (rt_device.cuh node_slot)
+        const int64_t n_rec = (n_nodes + 1) & ~(int64_t)1;
+        std::vector<float> dn((size_t)n_rec * 8, 0.0f);
+        for (int64_t k = 0; k < n_nodes; ++k) {
+            const rt_bvh_node& nd = ctx->nodes[k];
+            const int32_t code = nd.b == 0 ? nd.a : ~((nd.a << 3) | nd.b);
+            for (int c = 0; c < 3; ++c) { dn[node_slot((int)k, c)] = nd.bmin[c]; dn[node_slot((int)k, 4 + c)] = nd.bmax[c]; }
+            std::memcpy(&dn[node_slot((int)k, 3)], &code, 4);
+        }
+        CK(cudaMalloc(&ctx->d_nodes, dn.size() * sizeof(float)));
+        CK(cudaMemcpy(ctx->d_nodes, dn.data(), dn.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     const int m = ctx->m;
     if (m > 0) {

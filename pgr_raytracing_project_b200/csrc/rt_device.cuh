@@ -137,10 +137,45 @@ __device__ __forceinline__ void ldg_node(const float4* __restrict__ p, float4& l
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
         : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "l"(p));
 }
-__device__ __forceinline__ void ldg_pair(const float4* __restrict__ p, float4& l0, float4& l1, float4& r0, float4& r1) {
-    ldg_node(p, l0, l1);
-    ldg_node(p + 2, r0, r1);
+// ---- device node records (written by rt_api.cu ensure_device, rt_lbvh.cu k_device_nodes, rt_refit.cu k_finish).
+// Node k: box lo / hi + a code: code >= 0 = internal, index of the child pair (children code, code + 1); code <= -2 = leaf,
+// ~code = (first_slot << 3) | count.  Node 0 is the root, node 1 a pad record, siblings are nodes 2m, 2m + 1.
+// A sibling pair is stored INTERLEAVED in 64 aligned bytes (two 256-bit loads):
+//   float4 0: L.lo.x R.lo.x L.lo.y R.lo.y     float4 1: L.lo.z R.lo.z L.code R.code
+//   float4 2: L.hi.x R.hi.x L.hi.y R.hi.y     float4 3: L.hi.z R.hi.z 0      0
+// so that the same plane of the LEFT and the RIGHT child sit in one 64-bit register pair: the slab products of both children
+// are packed FFMA2 (fma.rn.f32x2, sm_100: two IEEE fmas per instruction, scalar operands broadcast) -- 6 instead of 12 issue
+// slots per traversal step, the same bits.  Everything that is not the traversal reads / writes nodes through node_slot().
+__host__ __device__ inline size_t node_slot(int k, int c) {           // c: 0..2 = lo.xyz, 3 = code, 4..6 = hi.xyz -> float index
+    return (size_t)(k >> 1) * 16 + (size_t)(c < 4 ? 2 * c : 8 + 2 * (c - 4)) + (size_t)(k & 1);
 }
+__device__ __forceinline__ int node_code(const float4* __restrict__ nodes, int k) {
+    return __float_as_int(reinterpret_cast<const float*>(nodes)[node_slot(k, 3)]);
+}
+__device__ __forceinline__ void node_read(const float4* __restrict__ nodes, int k, float lo[3], float hi[3], int& code) {
+    const float* f = reinterpret_cast<const float*>(nodes);
+    for (int c = 0; c < 3; ++c) { lo[c] = f[node_slot(k, c)]; hi[c] = f[node_slot(k, 4 + c)]; }
+    code = __float_as_int(f[node_slot(k, 3)]);
+}
+__device__ __forceinline__ void node_write(float4* __restrict__ nodes, int k, const float lo[3], const float hi[3], int code) {
+    float* f = reinterpret_cast<float*>(nodes);
+    for (int c = 0; c < 3; ++c) { f[node_slot(k, c)] = lo[c]; f[node_slot(k, 4 + c)] = hi[c]; }
+    f[node_slot(k, 3)] = __int_as_float(code);
+}
+// the root (node 0 = left record of pair 0) as a plain box: lo | code, hi | 0
+__device__ __forceinline__ void root_node(const float4* __restrict__ nodes, float4& lo, float4& hi) {
+    const float4 a = __ldg(nodes), b = __ldg(nodes + 1), c = __ldg(nodes + 2), d = __ldg(nodes + 3);
+    lo = make_float4(a.x, a.z, b.x, b.z);
+    hi = make_float4(c.x, c.z, d.x, 0.0f);
+}
+
+struct PairRec { float4 a, b, c, d; };                                 // the four float4 of a sibling pair (layout above)
+__device__ __forceinline__ void ldg_pair(const float4* __restrict__ p, PairRec& q) {
+    ldg_node(p, q.a, q.b);
+    ldg_node(p + 2, q.c, q.d);
+}
+__device__ __forceinline__ int pair_lc(const PairRec& q) { return __float_as_int(q.b.z); }
+__device__ __forceinline__ int pair_rc(const PairRec& q) { return __float_as_int(q.b.w); }
 
 __device__ __forceinline__ bool box_hit(const float4& lo, const float4& hi, const Ray& r, float tlo,
                                         float thi, float& tn) {
@@ -151,6 +186,22 @@ __device__ __forceinline__ bool box_hit(const float4& lo, const float4& hi, cons
     float f = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fminf(fmaxf(z1, z2), thi));
     tn = n;
     return n <= f;
+}
+
+// Both children of a pair against one ray: box_hit() of the left and of the right child, the six slab products of each plane pair
+// as ONE packed fma (x = left child, y = right child; the very values box_hit computes).
+__device__ __forceinline__ void pair_hit(const PairRec& q, const Ray& r, float tlo, float thi, bool& hl, bool& hr, float& tl, float& tr) {
+    const float2 ix = make_float2(r.ix, r.ix), iy = make_float2(r.iy, r.iy), iz = make_float2(r.iz, r.iz);
+    const float2 ax = make_float2(-r.ax, -r.ax), ay = make_float2(-r.ay, -r.ay), az = make_float2(-r.az, -r.az);
+    const float2 x1 = __ffma2_rn(make_float2(q.a.x, q.a.y), ix, ax), x2 = __ffma2_rn(make_float2(q.c.x, q.c.y), ix, ax);
+    const float2 y1 = __ffma2_rn(make_float2(q.a.z, q.a.w), iy, ay), y2 = __ffma2_rn(make_float2(q.c.z, q.c.w), iy, ay);
+    const float2 z1 = __ffma2_rn(make_float2(q.b.x, q.b.y), iz, az), z2 = __ffma2_rn(make_float2(q.d.x, q.d.y), iz, az);
+    const float nl = fmaxf(fmaxf(fminf(x1.x, x2.x), fminf(y1.x, y2.x)), fmaxf(fminf(z1.x, z2.x), tlo));
+    const float fl = fminf(fminf(fmaxf(x1.x, x2.x), fmaxf(y1.x, y2.x)), fminf(fmaxf(z1.x, z2.x), thi));
+    const float nr = fmaxf(fmaxf(fminf(x1.y, x2.y), fminf(y1.y, y2.y)), fmaxf(fminf(z1.y, z2.y), tlo));
+    const float fr = fminf(fminf(fmaxf(x1.y, x2.y), fmaxf(y1.y, y2.y)), fminf(fmaxf(z1.y, z2.y), thi));
+    tl = nl; tr = nr;
+    hl = nl <= fl; hr = nr <= fr;
 }
 
 // closest-hit update; ties go to the lower primitive number
@@ -313,7 +364,8 @@ template <bool TRI, bool STATS>
 __device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit& h, Counters& cnt, bool cam) {
     h.t = kTMax; h.prim = -1; h.slot = -1;
     if (sc.n_nodes == 0) return;
-    float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
+    float4 lo, hi;
+    root_node(sc.nodes, lo, hi);
     float tn;
     if (STATS) cnt.nodes += 1;
     if (!box_hit(lo, hi, r, kTMin, h.t, tn)) return;
@@ -323,14 +375,13 @@ __device__ __forceinline__ void intersect(const SceneView& sc, const Ray& r, Hit
     int sp = 0;
     for (;;) {
         if (cur >= 0) {
-            const float4* p = sc.nodes + 2 * (size_t)cur;
-            float4 l0, l1, r0, r1;
-            ldg_pair(p, l0, l1, r0, r1);
+            PairRec q;
+            ldg_pair(sc.nodes + 2 * (size_t)cur, q);
             if (STATS) cnt.nodes += 2;
             float tl, tr;
-            bool hl = box_hit(l0, l1, r, kTMin, h.t, tl);
-            bool hr = box_hit(r0, r1, r, kTMin, h.t, tr);
-            int lc = __float_as_int(l0.w), rc = __float_as_int(r0.w);
+            bool hl, hr;
+            pair_hit(q, r, kTMin, h.t, hl, hr, tl, tr);
+            int lc = pair_lc(q), rc = pair_rc(q);
             if (hl && hr) {
                 if (tr < tl) { int c = lc; lc = rc; rc = c; float tf = tl; tl = tr; tr = tf; }
                 stack_code[sp] = rc; stack_tn[sp] = tr; ++sp;
@@ -405,7 +456,8 @@ __device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Tr
     tv.h.t = kTMax; tv.h.prim = -1; tv.h.slot = -1;
     tv.sp = 0; tv.cur = kDone;
     if (sc.n_nodes == 0) return;
-    float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
+    float4 lo, hi;
+    root_node(sc.nodes, lo, hi);
     float tn;
     if (STATS) cnt.nodes += 1;
     if (box_hit(lo, hi, r, kTMin, tv.h.t, tn)) tv.cur = two_t > 0 ? 0 : __float_as_int(lo.w);
@@ -445,22 +497,21 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
                 tv.cur = kNeedPop;
             }
         } else if (is_int) {
-            float4 l0, l1, r0, r1;
+            PairRec q;
             int lc, rc;
             if (TREELET && tv.cur < two_t) {                  // per lane: top of the tree out of shared memory
                 const float4* p = s_tree + 2 * tv.cur;
-                l0 = p[0]; l1 = p[1]; r0 = p[2]; r1 = p[3];
-                lc = __float_as_int(l0.w); rc = __float_as_int(r0.w);
+                q.a = p[0]; q.b = p[1]; q.c = p[2]; q.d = p[3];
+                lc = pair_lc(q); rc = pair_rc(q);
             } else {
-                const float4* p = sc.nodes + 2 * (size_t)(TREELET ? tv.cur - two_t : tv.cur);
-                ldg_pair(p, l0, l1, r0, r1);
-                lc = __float_as_int(l0.w); rc = __float_as_int(r0.w);
+                ldg_pair(sc.nodes + 2 * (size_t)(TREELET ? tv.cur - two_t : tv.cur), q);
+                lc = pair_lc(q); rc = pair_rc(q);
                 if (TREELET) { lc = lc >= 0 ? lc + two_t : lc; rc = rc >= 0 ? rc + two_t : rc; }
             }
             if (STATS) cnt.nodes += 2;
             float tl, tr;
-            bool hl = box_hit(l0, l1, r, kTMin, tv.h.t, tl);
-            bool hr = box_hit(r0, r1, r, kTMin, tv.h.t, tr);
+            bool hl, hr;
+            pair_hit(q, r, kTMin, tv.h.t, hl, hr, tl, tr);
             if (hl && hr) {
                 if (tr < tl) { int c = lc; lc = rc; rc = c; float tf = tl; tl = tr; tr = tf; }
                 st.put(tv.sp, rc, tr); ++tv.sp;
@@ -491,17 +542,22 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
 // no component is tiny, so the near / far plane of each slab is known at compile time and the slab
 // test needs no per-axis min / max (4 instead of 10 FMNMX-pipe instructions per box; that pipe, not
 // FFMA, limits the traversal).  fmaf is monotonic, so picking the plane by sign gives exactly the
-// value fminf / fmaxf would pick: same bits as box_hit().  OCT = 8: generic test.
+// value fminf / fmaxf would pick: same bits as box_hit().  OCT = 8: generic test.  Both children of a pair are tested at once
+// (pair_hit_oct): their slab products are packed fmas over the interleaved pair record.
 template <int OCT>
-__device__ __forceinline__ bool box_hit_oct(const float4& lo, const float4& hi, const Ray& r, float tlo, float thi, float& tn) {
-    if (OCT == 8) return box_hit(lo, hi, r, tlo, thi, tn);
-    const float nx = (OCT & 1) ? hi.x : lo.x, fx = (OCT & 1) ? lo.x : hi.x;
-    const float ny = (OCT & 2) ? hi.y : lo.y, fy = (OCT & 2) ? lo.y : hi.y;
-    const float nz = (OCT & 4) ? hi.z : lo.z, fz = (OCT & 4) ? lo.z : hi.z;
-    float n = fmaxf(fmaxf(__fmaf_rn(nx, r.ix, -r.ax), __fmaf_rn(ny, r.iy, -r.ay)), fmaxf(__fmaf_rn(nz, r.iz, -r.az), tlo));
-    float f = fminf(fminf(__fmaf_rn(fx, r.ix, -r.ax), __fmaf_rn(fy, r.iy, -r.ay)), fminf(__fmaf_rn(fz, r.iz, -r.az), thi));
-    tn = n;
-    return n <= f;
+__device__ __forceinline__ void pair_hit_oct(const PairRec& q, const Ray& r, float tlo, float thi, bool& hl, bool& hr, float& tl, float& tr) {
+    if (OCT == 8) { pair_hit(q, r, tlo, thi, hl, hr, tl, tr); return; }
+    const float2 ix = make_float2(r.ix, r.ix), iy = make_float2(r.iy, r.iy), iz = make_float2(r.iz, r.iz);
+    const float2 ax = make_float2(-r.ax, -r.ax), ay = make_float2(-r.ay, -r.ay), az = make_float2(-r.az, -r.az);
+    const float2 lox = make_float2(q.a.x, q.a.y), loy = make_float2(q.a.z, q.a.w), loz = make_float2(q.b.x, q.b.y);
+    const float2 hix = make_float2(q.c.x, q.c.y), hiy = make_float2(q.c.z, q.c.w), hiz = make_float2(q.d.x, q.d.y);
+    const float2 nx = __ffma2_rn((OCT & 1) ? hix : lox, ix, ax), fx = __ffma2_rn((OCT & 1) ? lox : hix, ix, ax);
+    const float2 ny = __ffma2_rn((OCT & 2) ? hiy : loy, iy, ay), fy = __ffma2_rn((OCT & 2) ? loy : hiy, iy, ay);
+    const float2 nz = __ffma2_rn((OCT & 4) ? hiz : loz, iz, az), fz = __ffma2_rn((OCT & 4) ? loz : hiz, iz, az);
+    const float nl = fmaxf(fmaxf(nx.x, ny.x), fmaxf(nz.x, tlo)), fl = fminf(fminf(fx.x, fy.x), fminf(fz.x, thi));
+    const float nr = fmaxf(fmaxf(nx.y, ny.y), fmaxf(nz.y, tlo)), fr = fminf(fminf(fx.y, fy.y), fminf(fz.y, thi));
+    tl = nl; tr = nr;
+    hl = nl <= fl; hr = nr <= fr;
 }
 
 // TREELET (shared-memory staging of the top treelet, north_star): s_tree = the top levels of the tree staged in shared
@@ -515,23 +571,22 @@ __device__ __forceinline__ void packet_walk(const SceneView& sc, const float4* _
     int sp = 0;
     for (;;) {
         if (cur >= 0) {
-            float4 l0, l1, r0, r1;
+            PairRec q;
             int lc, rc;
             if (TREELET && cur < two_t) {
                 const float4* p = s_tree + 2 * cur;
-                l0 = p[0]; l1 = p[1]; r0 = p[2]; r1 = p[3];
-                lc = __float_as_int(l0.w); rc = __float_as_int(r0.w);
+                q.a = p[0]; q.b = p[1]; q.c = p[2]; q.d = p[3];
+                lc = pair_lc(q); rc = pair_rc(q);
             } else {
-                const float4* p = sc.nodes + 2 * (size_t)(TREELET ? cur - two_t : cur);
-                ldg_pair(p, l0, l1, r0, r1);
-                lc = __float_as_int(l0.w); rc = __float_as_int(r0.w);
+                ldg_pair(sc.nodes + 2 * (size_t)(TREELET ? cur - two_t : cur), q);
+                lc = pair_lc(q); rc = pair_rc(q);
                 if (TREELET) { lc = lc >= 0 ? lc + two_t : lc; rc = rc >= 0 ? rc + two_t : rc; }
             }
             if (STATS && lane == 0) cnt.nodes += 2;
             work += 1;
             float tl, tr;
-            const bool hl = box_hit_oct<OCT>(l0, l1, r, kTMin, h.t, tl);
-            const bool hr = box_hit_oct<OCT>(r0, r1, r, kTMin, h.t, tr);
+            bool hl, hr;
+            pair_hit_oct<OCT>(q, r, kTMin, h.t, hl, hr, tl, tr);
             const unsigned bl = __ballot_sync(0xffffffffu, hl), br = __ballot_sync(0xffffffffu, hr);
             if (bl != 0u && br != 0u) {
                 // entry distances with +inf for a missed child: a lane votes "right first" iff tr' < tl'
@@ -572,7 +627,8 @@ __device__ __forceinline__ void packet_intersect(const SceneView& sc, const floa
                                                  int& work, const float4* s_tree = nullptr) {
     h.t = active ? kTMax : 0.0f; h.prim = -1; h.slot = -1;
     if (sc.n_nodes == 0) return;
-    const float4 lo = __ldg(sc.nodes), hi = __ldg(sc.nodes + 1);
+    float4 lo, hi;
+    root_node(sc.nodes, lo, hi);
     float tn;
     if (STATS && lane == 0) cnt.nodes += 1;
     const bool hit = box_hit(lo, hi, r, kTMin, h.t, tn);

@@ -322,24 +322,26 @@ __global__ void __launch_bounds__(256)
 k_build_treelet(const float4* __restrict__ nodes, int n_pairs, float4* __restrict__ out) {
     const int two_t = 2 * n_pairs;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n_pairs; s += gridDim.x * blockDim.x) {
-        int g = __float_as_int(nodes[0].w);                    // the root's child pair (the root is internal: checked by the host)
+        int g = node_code(nodes, 0);                           // the root's child pair (the root is internal: checked by the host)
         const unsigned path = (unsigned)s + 1u;                // 1-based heap index: the bits below the leading one, top down
         bool exists = true;
         for (int bit = 30 - __clz(path); bit >= 0 && exists; --bit) {
             const int side = (path >> bit) & 1u;
-            const int c = __float_as_int(nodes[2 * (size_t)(g + side)].w);
+            const int c = node_code(nodes, g + side);
             if (c < 0) exists = false; else g = c;
         }
-        float4 rec[4] = {make_float4(0, 0, 0, __int_as_float(-1)), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, __int_as_float(-1)), make_float4(0, 0, 0, 0)};
+        // a pair record as the traversal reads it (rt_device.cuh: interleaved; the two codes are .z / .w of the second float4)
+        float4 rec[4] = {make_float4(0, 0, 0, 0), make_float4(0, 0, __int_as_float(-1), __int_as_float(-1)), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0)};
         if (exists) {
             for (int k = 0; k < 4; ++k) rec[k] = nodes[2 * (size_t)g + k];
+            int code[2] = {__float_as_int(rec[1].z), __float_as_int(rec[1].w)};
             for (int side = 0; side < 2; ++side) {
-                const int c = __float_as_int(rec[2 * side].w);
-                if (c >= 0) {
+                if (code[side] >= 0) {
                     const int child = 2 * s + 1 + side;
-                    rec[2 * side].w = __int_as_float(child < n_pairs ? 2 * child : c + two_t);
+                    code[side] = child < n_pairs ? 2 * child : code[side] + two_t;
                 }
             }
+            rec[1].z = __int_as_float(code[0]); rec[1].w = __int_as_float(code[1]);
         }
         for (int k = 0; k < 4; ++k) out[4 * (size_t)s + k] = rec[k];
     }

@@ -232,11 +232,11 @@ __global__ void k_emit_tiny(const float* __restrict__ lo, const float* __restric
 
 // ABI records -> device records (code in .a, see rt_device.cuh) and primitive records in leaf order
 __global__ void k_device_nodes(const rt_bvh_node* __restrict__ abi, int n_nodes, rt_bvh_node* __restrict__ dev) {
+    float4* nodes = reinterpret_cast<float4*>(dev);                    // sibling pairs interleaved (rt_device.cuh node_slot)
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_nodes; k += gridDim.x * blockDim.x) {
-        rt_bvh_node nd = abi[k];
-        nd.a = nd.b == 0 ? nd.a : ~((nd.a << 3) | nd.b);
-        nd.b = 0;
-        dev[k] = nd;
+        const rt_bvh_node nd = abi[k];
+        node_write(nodes, k, nd.bmin, nd.bmax, nd.b == 0 ? nd.a : ~((nd.a << 3) | nd.b));
+        if (k & 1) { float* f = reinterpret_cast<float*>(nodes) + (size_t)(k >> 1) * 16; f[14] = 0.0f; f[15] = 0.0f; }
     }
 }
 

@@ -44,7 +44,7 @@ __global__ void k_parents(const float4* __restrict__ nodes, int n_nodes, int* __
         flag[k] = 0;
         if (k == 0) parent[0] = -1;
         if (k == 1) continue;                                           // pad record
-        const int code = __float_as_int(nodes[2 * (size_t)k].w);
+        const int code = node_code(nodes, k);
         if (code >= 0) { parent[code] = k; parent[code + 1] = k; }
     }
 }
@@ -54,7 +54,7 @@ __global__ void k_fit(const float4* __restrict__ nodes, int n_nodes, const int* 
                       int is_tri, const int* __restrict__ parent, int* __restrict__ flag, float* __restrict__ box) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_nodes; k += gridDim.x * blockDim.x) {
         if (k == 1) continue;
-        const int code = __float_as_int(nodes[2 * (size_t)k].w);
+        const int code = node_code(nodes, k);
         if (code >= 0) continue;                                        // internal: filled in by its second child
         const int first = (~code) >> 3, count = (~code) & 7;
         float b[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -102,11 +102,10 @@ __global__ void k_finish(const float* __restrict__ box, int n_nodes, float4* __r
             abi[1] = nd;
             continue;
         }
-        const int code = __float_as_int(nodes[2 * (size_t)k].w);
+        const int code = node_code(nodes, k);
         float lo[3], hi[3];
         for (int c = 0; c < 3; ++c) { lo[c] = __fsub_rn(box[6 * (size_t)k + c], pad); hi[c] = __fadd_rn(box[6 * (size_t)k + 3 + c], pad); }
-        nodes[2 * (size_t)k] = make_float4(lo[0], lo[1], lo[2], __int_as_float(code));
-        nodes[2 * (size_t)k + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        node_write(nodes, k, lo, hi, code);
         for (int c = 0; c < 3; ++c) { nd.bmin[c] = lo[c]; nd.bmax[c] = hi[c]; }
         if (code >= 0) { nd.a = code; nd.b = 0; }
         else { nd.a = (~code) >> 3; nd.b = (~code) & 7; }
@@ -119,9 +118,11 @@ __global__ void k_area(const float4* __restrict__ nodes, int n_nodes, double* __
     double part = 0.0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_nodes; k += gridDim.x * blockDim.x) {
         if (k == 1) continue;
-        const float4 lo = nodes[2 * (size_t)k], hi = nodes[2 * (size_t)k + 1];
-        if (__float_as_int(lo.w) < 0) continue;
-        const double ex = (double)hi.x - lo.x, ey = (double)hi.y - lo.y, ez = (double)hi.z - lo.z;
+        float lo[3], hi[3];
+        int code;
+        node_read(nodes, k, lo, hi, code);
+        if (code < 0) continue;
+        const double ex = (double)hi[0] - lo[0], ey = (double)hi[1] - lo[1], ez = (double)hi[2] - lo[2];
         part += ex * ey + ey * ez + ez * ex;
     }
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
