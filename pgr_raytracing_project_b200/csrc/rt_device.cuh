@@ -261,9 +261,26 @@ __device__ __forceinline__ void test_cam_tri_records(const float4& r0, const flo
 __device__ __forceinline__ bool cam_tri_inside(const float4& r0, const float4& r1, const float4& r2, const Ray& r) {
     return tri_inside(dot3(r.dx, r.dy, r.dz, r0.x, r0.y, r0.z), dot3(r.dx, r.dy, r.dz, r1.x, r1.y, r1.z), dot3(r.dx, r.dy, r.dz, r2.x, r2.y, r2.z));
 }
+// The per-camera TABLE in global memory (k_cam_tris) holds the record re-packed so that det and u*det -- two dot products with
+// the same direction -- are one chain of packed fmas (FFMA2: 3 issue slots instead of 6; the same bits as two dot3):
+//   A = (r0.x, r1.x, r0.y, r1.y)   B = (r0.z, r1.z, r2.x, r2.y)   C = (r2.z, e2.(s x e1), prim, material)
+__device__ __forceinline__ void cam_tri_pack(const float4& r0, const float4& r1, const float4& r2, float4& A, float4& B, float4& C) {
+    A = make_float4(r0.x, r1.x, r0.y, r1.y);
+    B = make_float4(r0.z, r1.z, r2.x, r2.y);
+    C = make_float4(r2.z, r0.w, r1.w, r2.w);
+}
 __device__ __forceinline__ void test_cam_tri_packet(const float4* __restrict__ cam_prims, int slot, const Ray& r, Hit& h) {
     const float4* p = cam_prims + 3 * (size_t)slot;
-    test_cam_tri_records(__ldg(p), __ldg(p + 1), __ldg(p + 2), slot, r, h);
+    const float4 A = __ldg(p), B = __ldg(p + 1), C = __ldg(p + 2);
+    float2 du = __fmul2_rn(make_float2(A.x, A.y), make_float2(r.dx, r.dx));
+    du = __ffma2_rn(make_float2(A.z, A.w), make_float2(r.dy, r.dy), du);
+    du = __ffma2_rn(make_float2(B.x, B.y), make_float2(r.dz, r.dz), du);
+    float vn = __fmaf_rn(r.dz, C.x, __fmaf_rn(r.dy, B.w, __fmul_rn(r.dx, B.z)));
+    // tri_accept() with det and u*det still packed: the sign flip of the pair is one instruction
+    const float sg = du.x < 0.0f ? -1.0f : 1.0f;
+    du = __fmul2_rn(du, make_float2(sg, sg)); vn = __fmul_rn(vn, sg);
+    if (du.x > 0.0f && du.y >= 0.0f && vn >= 0.0f && __fadd_rn(du.y, vn) <= du.x)
+        consider(h, __fdiv_rn(__fmul_rn(C.y, sg), du.x), __float_as_int(C.z), slot);
 }
 
 // any-ray route (records v0 | prim, e1 | material, e2 | 0 already in registers)

@@ -219,10 +219,11 @@ __global__ void __launch_bounds__(256)
 k_cam_tris(const float4* __restrict__ prims, float4* __restrict__ cam_prims, int n, float ox, float oy, float oz) {
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
         const float4* p = prims + kTriStride * (size_t)slot;
-        float4 r0, r1, r2;
+        float4 r0, r1, r2, A, B, C;
         cam_tri_record(__ldg(p), __ldg(p + 1), __ldg(p + 2), ox, oy, oz, r0, r1, r2);
+        cam_tri_pack(r0, r1, r2, A, B, C);
         float4* o = cam_prims + 3 * (size_t)slot;
-        o[0] = r0; o[1] = r1; o[2] = r2;
+        o[0] = A; o[1] = B; o[2] = C;
     }
 }
 
