@@ -65,23 +65,112 @@ __device__ __forceinline__ unsigned smem_append(unsigned* counter, bool pred, in
 
 // Closest hit of ray r over all n primitives in shared memory (see the header: inside pass, then the full test on the
 // primitives of the mask).  CAM: camera ray (triangles: per-camera table route).
+// Pass 1 for triangles, TWO TRIANGLES PER INSTRUCTION: the records of triangles 2j and 2j + 1 are staged interleaved
+// (s_pair, 6 float4 per pair: v0, e1, -e1, e2 for the any-ray test; s_cpair, 5 float4: the three table vectors for the camera-ray
+// test), so every product / fma of the inside test is one packed FFMA2 / FMUL2 over the pair (the ray's components broadcast) --
+// the arithmetic of tri_mt_inside / cam_tri_inside operation by operation, half the issue slots.
+constexpr int kPairF4 = 6, kCPairF4 = 5;
+
+__device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }
+__device__ __forceinline__ float2 dot3_2(const float2& ax, const float2& ay, const float2& az, const float2& bx, const float2& by, const float2& bz) {
+    return __ffma2_rn(az, bz, __ffma2_rn(ay, by, __fmul2_rn(ax, bx)));
+}
+
+// tri_inside() of both triangles of the pair, the sign flips and the u + v sum packed: bit 0 = first, bit 1 = second triangle
+__device__ __forceinline__ unsigned tri_inside2(float2 det, float2 un, float2 vn) {
+    const float2 sg = make_float2(det.x < 0.0f ? -1.0f : 1.0f, det.y < 0.0f ? -1.0f : 1.0f);
+    det = __fmul2_rn(det, sg); un = __fmul2_rn(un, sg); vn = __fmul2_rn(vn, sg);
+    const float2 uv = __fadd2_rn(un, vn);
+    return ((det.x > 0.0f && un.x >= 0.0f && vn.x >= 0.0f && uv.x <= det.x) ? 1u : 0u) |
+           ((det.y > 0.0f && un.y >= 0.0f && vn.y >= 0.0f && uv.y <= det.y) ? 2u : 0u);
+}
+
+// any-ray inside test of the pair: bit 0 = triangle 2j, bit 1 = triangle 2j + 1
+__device__ __forceinline__ unsigned pair_mt_inside(const float4* p, const Ray& r) {
+    const float4 P0 = p[0], P1 = p[1], P2 = p[2], P3 = p[3], P4 = p[4], P5 = p[5];
+    const float2 v0x = make_float2(P0.x, P0.y), v0y = make_float2(P0.z, P0.w), v0z = make_float2(P1.x, P1.y);
+    const float2 e1x = make_float2(P1.z, P1.w), e1y = make_float2(P2.x, P2.y), e1z = make_float2(P2.z, P2.w);
+    const float2 n1x = make_float2(P3.x, P3.y), n1y = make_float2(P3.z, P3.w), n1z = make_float2(P4.x, P4.y);     // -e1
+    const float2 e2x = make_float2(P4.z, P4.w), e2y = make_float2(P5.x, P5.y), e2z = make_float2(P5.z, P5.w);
+    // p = d x e2 (cross3: fma(ay, bz, -(az * by)), ...), the negated product as (-az) * by
+    const float2 px = __ffma2_rn(e2z, bc(r.dy), __fmul2_rn(e2y, bc(-r.dz)));
+    const float2 py = __ffma2_rn(e2x, bc(r.dz), __fmul2_rn(e2z, bc(-r.dx)));
+    const float2 pz = __ffma2_rn(e2y, bc(r.dx), __fmul2_rn(e2x, bc(-r.dy)));
+    const float2 det = dot3_2(e1x, e1y, e1z, px, py, pz);
+    const float2 sx = __ffma2_rn(v0x, bc(-1.0f), bc(r.ox)), sy = __ffma2_rn(v0y, bc(-1.0f), bc(r.oy)), sz = __ffma2_rn(v0z, bc(-1.0f), bc(r.oz));
+    const float2 un = dot3_2(sx, sy, sz, px, py, pz);
+    // q = s x e1, the negated product as az * (-by)
+    const float2 qx = __ffma2_rn(sy, e1z, __fmul2_rn(sz, n1y));
+    const float2 qy = __ffma2_rn(sz, e1x, __fmul2_rn(sx, n1z));
+    const float2 qz = __ffma2_rn(sx, e1y, __fmul2_rn(sy, n1x));
+    const float2 vn = dot3_2(bc(r.dx), bc(r.dy), bc(r.dz), qx, qy, qz);
+    return tri_inside2(det, un, vn);
+}
+
+// camera-ray inside test of the pair (table vectors r0, r1, r2 of both triangles interleaved)
+__device__ __forceinline__ unsigned pair_cam_inside(const float4* p, const Ray& r) {
+    const float4 P0 = p[0], P1 = p[1], P2 = p[2], P3 = p[3], P4 = p[4];
+    const float2 dx = bc(r.dx), dy = bc(r.dy), dz = bc(r.dz);
+    const float2 det = dot3_2(dx, dy, dz, make_float2(P0.x, P0.y), make_float2(P0.z, P0.w), make_float2(P1.x, P1.y));
+    const float2 un = dot3_2(dx, dy, dz, make_float2(P1.z, P1.w), make_float2(P2.x, P2.y), make_float2(P2.z, P2.w));
+    const float2 vn = dot3_2(dx, dy, dz, make_float2(P3.x, P3.y), make_float2(P3.z, P3.w), make_float2(P4.x, P4.y));
+    return tri_inside2(det, un, vn);
+}
+
+// interleave component c of two float4-record triangles into a pair array (staging)
+__device__ __forceinline__ void stage_pair_mt(const float4* s_prims, int n, int j, float4* out) {
+    const int a = 2 * j, b = 2 * j + 1;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 av0 = s_prims[3 * a], ae1 = s_prims[3 * a + 1], ae2 = s_prims[3 * a + 2];
+    const float4 bv0 = b < n ? s_prims[3 * b] : z, be1 = b < n ? s_prims[3 * b + 1] : z, be2 = b < n ? s_prims[3 * b + 2] : z;   // odd n: a null triangle
+    out[0] = make_float4(av0.x, bv0.x, av0.y, bv0.y);
+    out[1] = make_float4(av0.z, bv0.z, ae1.x, be1.x);
+    out[2] = make_float4(ae1.y, be1.y, ae1.z, be1.z);
+    out[3] = make_float4(-ae1.x, -be1.x, -ae1.y, -be1.y);
+    out[4] = make_float4(-ae1.z, -be1.z, ae2.x, be2.x);
+    out[5] = make_float4(ae2.y, be2.y, ae2.z, be2.z);
+}
+__device__ __forceinline__ void stage_pair_cam(const float4* s_cam, int n, int j, float4* out) {
+    const int a = 2 * j, b = 2 * j + 1;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a0 = s_cam[3 * a], a1 = s_cam[3 * a + 1], a2 = s_cam[3 * a + 2];
+    const float4 b0 = b < n ? s_cam[3 * b] : z, b1 = b < n ? s_cam[3 * b + 1] : z, b2 = b < n ? s_cam[3 * b + 2] : z;
+    out[0] = make_float4(a0.x, b0.x, a0.y, b0.y);
+    out[1] = make_float4(a0.z, b0.z, a1.x, b1.x);
+    out[2] = make_float4(a1.y, b1.y, a1.z, b1.z);
+    out[3] = make_float4(a2.x, b2.x, a2.y, b2.y);
+    out[4] = make_float4(a2.z, b2.z, 0.f, 0.f);
+}
+
 template <bool TRI, bool CAM>
-__device__ __forceinline__ void tiny_closest(const float4* s_prims, const float4* s_cam, const int* s_slot_prim, int n, const Ray& r, Hit& h) {
+__device__ __forceinline__ void tiny_closest(const float4* s_prims, const float4* s_cam, const int* s_slot_prim, const float4* s_pair,
+                                             const float4* s_cpair, int n, const Ray& r, Hit& h) {
     h.t = kTMax; h.prim = -1; h.slot = -1;
     unsigned m[2] = {0u, 0u};
+    if (TRI) {
+        const int n_pairs = (n + 1) >> 1;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        const int k0 = half * 32, k1 = n < k0 + 32 ? n : k0 + 32;
-        unsigned bit = 1u, mm = 0u;
-#pragma unroll 4
-        for (int k = k0; k < k1; ++k, bit <<= 1) {
-            bool in;
-            if (TRI) in = CAM ? cam_tri_inside(s_cam[3 * k], s_cam[3 * k + 1], s_cam[3 * k + 2], r)
-                              : tri_mt_inside(s_prims[3 * k], s_prims[3 * k + 1], s_prims[3 * k + 2], r);
-            else in = sphere_maybe(s_prims[k], r);
-            if (in) mm |= bit;
+        for (int half = 0; half < 2; ++half) {
+            const int j0 = half * 16, j1 = n_pairs < j0 + 16 ? n_pairs : j0 + 16;
+            unsigned mm = 0u;
+            int sh = 0;
+#pragma unroll 2
+            for (int j = j0; j < j1; ++j, sh += 2) {
+                const unsigned in = CAM ? pair_cam_inside(s_cpair + kCPairF4 * j, r) : pair_mt_inside(s_pair + kPairF4 * j, r);
+                mm |= in << sh;
+            }
+            m[half] = mm;
         }
-        m[half] = mm;
+    } else {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int k0 = half * 32, k1 = n < k0 + 32 ? n : k0 + 32;
+            unsigned bit = 1u, mm = 0u;
+#pragma unroll 4
+            for (int k = k0; k < k1; ++k, bit <<= 1)
+                if (sphere_maybe(s_prims[k], r)) mm |= bit;
+            m[half] = mm;
+        }
     }
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -105,6 +194,8 @@ k_tiny(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
     __shared__ float4 s_cam[TRI ? kTinyMaxPrims * 3 : 1];
     __shared__ int s_slot_prim[kTinyMaxPrims];
     __shared__ float4 s_mats[kTinyMaxMats * 2];
+    __shared__ float4 s_pair[TRI ? (kTinyMaxPrims / 2) * kPairF4 : 1];     // triangle pairs, interleaved (pair_mt_inside)
+    __shared__ float4 s_cpair[TRI ? (kTinyMaxPrims / 2) * kCPairF4 : 1];   // camera-table pairs (pair_cam_inside)
     __shared__ float4 q_o[2][THREADS];            // origin | path id
     __shared__ float4 q_d[2][THREADS];            // direction | throughput.r
     __shared__ float2 q_t[2][THREADS];            // throughput.g, throughput.b
@@ -124,6 +215,11 @@ k_tiny(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
         for (int k = tid; k < n; k += THREADS)
             cam_tri_record(s_prims[3 * k], s_prims[3 * k + 1], s_prims[3 * k + 2], cam.px, cam.py, cam.pz, s_cam[3 * k], s_cam[3 * k + 1],
                            s_cam[3 * k + 2]);
+        __syncthreads();
+        for (int j = tid; j < (n + 1) / 2; j += THREADS) {
+            stage_pair_mt(s_prims, n, j, s_pair + kPairF4 * j);
+            stage_pair_cam(s_cam, n, j, s_cpair + kCPairF4 * j);
+        }
     }
     SceneView ss = sc;                            // the shading helpers read prims / mats through this view: shared memory
     ss.prims = s_prims; ss.mats = s_mats; ss.slot_prim = s_slot_prim;
@@ -165,7 +261,7 @@ k_tiny(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
                     const uint4 ctl = philox4x32_10(pixel, sample, 0u, 0u, a.k0, a.k1);
                     r = camera_ray(cam, p.i, p.j, u01(ctl.x), u01(ctl.y), inv_w, inv_h);
                     Hit h;
-                    tiny_closest<TRI, true>(s_prims, s_cam, s_slot_prim, n, r, h);
+                    tiny_closest<TRI, true>(s_prims, s_cam, s_slot_prim, s_pair, s_cpair, n, r, h);
                     if (STATS) { st_rays += 1; st_seg += 1; }
                     if (h.prim < 0) {
                         cr = __fmaf_rn(tr, sc.bg_r, cr); cg = __fmaf_rn(tg, sc.bg_g, cg); cb = __fmaf_rn(tb, sc.bg_b, cb);
@@ -203,7 +299,7 @@ k_tiny(const __grid_constant__ SceneView sc, const __grid_constant__ CameraBlock
                         tr = d.w; tg = t2.x; tb = t2.y;
                         r.ox = o.x; r.oy = o.y; r.oz = o.z; r.dx = d.x; r.dy = d.y; r.dz = d.z;
                         Hit h;
-                        tiny_closest<TRI, false>(s_prims, s_cam, s_slot_prim, n, r, h);
+                        tiny_closest<TRI, false>(s_prims, s_cam, s_slot_prim, s_pair, s_cpair, n, r, h);
                         if (STATS) st_seg += 1;
                         float cr = s_rad[0][pid], cg = s_rad[1][pid], cb = s_rad[2][pid];
                         if (h.prim < 0) {
@@ -264,6 +360,8 @@ k_tiny_lockstep(const __grid_constant__ SceneView sc, const __grid_constant__ Ca
     __shared__ float4 s_cam[TRI ? kTinyMaxPrims * 3 : 1];
     __shared__ int s_slot_prim[kTinyMaxPrims];
     __shared__ float4 s_mats[kTinyMaxMats * 2];
+    __shared__ float4 s_pair[TRI ? (kTinyMaxPrims / 2) * kPairF4 : 1];
+    __shared__ float4 s_cpair[TRI ? (kTinyMaxPrims / 2) * kCPairF4 : 1];
     const int tid = threadIdx.x, lane = tid & 31;
     const int n = a.n;
     for (int k = tid; k < n * (TRI ? kTriStride : 1); k += THREADS) s_prims[k] = __ldg(sc.prims + k);
@@ -274,6 +372,11 @@ k_tiny_lockstep(const __grid_constant__ SceneView sc, const __grid_constant__ Ca
         for (int k = tid; k < n; k += THREADS)
             cam_tri_record(s_prims[3 * k], s_prims[3 * k + 1], s_prims[3 * k + 2], cam.px, cam.py, cam.pz, s_cam[3 * k], s_cam[3 * k + 1],
                            s_cam[3 * k + 2]);
+        __syncthreads();
+        for (int j = tid; j < (n + 1) / 2; j += THREADS) {
+            stage_pair_mt(s_prims, n, j, s_pair + kPairF4 * j);
+            stage_pair_cam(s_cam, n, j, s_cpair + kCPairF4 * j);
+        }
     }
     __syncthreads();
     SceneView ss = sc;
@@ -302,8 +405,8 @@ k_tiny_lockstep(const __grid_constant__ SceneView sc, const __grid_constant__ Ca
                 if (!__any_sync(0xffffffffu, alive)) break;
                 if (alive) {
                     Hit h;
-                    if (b == 0) tiny_closest<TRI, true>(s_prims, s_cam, s_slot_prim, n, r, h);
-                    else tiny_closest<TRI, false>(s_prims, s_cam, s_slot_prim, n, r, h);
+                    if (b == 0) tiny_closest<TRI, true>(s_prims, s_cam, s_slot_prim, s_pair, s_cpair, n, r, h);
+                    else tiny_closest<TRI, false>(s_prims, s_cam, s_slot_prim, s_pair, s_cpair, n, r, h);
                     if (STATS) st_seg += 1;
                     alive = false;
                     if (h.prim < 0) {
