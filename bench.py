@@ -634,6 +634,10 @@ def main():
             "config": bench_config(world, exchange_mode, barrier_mode),
             "scene": {"bvh_nodes": int(len(nodes)), "host_bvh_build_plus_upload_s": round(build_s, 2)},
             "frame_matches_1gpu": frame_matches_1gpu, "host_frame_matches_1gpu": host_frame_matches_1gpu,
+            "parity_pin": "the reference has no triangle primitive, so this workload is pinned to the repo's own CPU oracle (GPU == oracle bit for "
+                          "bit on the timed frame: cpu_baseline.frame_matches_gpu; oracle == float64 Moller-Trumbore and brute force in tests/); the "
+                          "REAL reference is the yardstick on the 1M-sphere twin (sphere_twin.vs_reference_v1; ids identical but for the "
+                          "reference's own grazing hits, distances within 1e-5: tests/test_gpu_parity.py::test_sphere_twin_vs_v1_reference)",
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 112, "d2h_bytes_per_step": W * H * 3 * 4,
                     "ms_per_step": float(e2e_t.item()) / args.steps * 1e3, "api": e2e_api},

@@ -10,11 +10,16 @@ struct PixelWork { int i, j, out_index; bool active; };
 
 // Decode work item `w` (one 8x4 pixel block) for this lane.
 __device__ __forceinline__ PixelWork decode_work(const TileMap& tm, int w, int lane) {
-    int bx = tm.tile_w >> 3;
-    int per_tile = bx * (tm.tile_h >> 2);
-    int k = w / per_tile;                 // local tile number
-    int sub = w - k * per_tile;
-    int sy = sub / bx, sx = sub - sy * bx;
+    int k, sy, sx;                        // local tile number, block row / column inside the tile
+    if (tm.tile_w == 32 && tm.tile_h == 32) {             // the library's own tiles: shifts instead of two integer divisions
+        k = w >> 5; sy = (w >> 2) & 7; sx = w & 3;
+    } else {
+        int bx = tm.tile_w >> 3;
+        int per_tile = bx * (tm.tile_h >> 2);
+        k = w / per_tile;
+        int sub = w - k * per_tile;
+        sy = sub / bx; sx = sub - sy * bx;
+    }
     int tile = tm.first_tile + k * tm.tile_stride;
     int ty = tile / tm.tiles_x, tx = tile - ty * tm.tiles_x;
     if (tm.skew) tx = (tx + tm.skew * ty) % tm.tiles_x;
