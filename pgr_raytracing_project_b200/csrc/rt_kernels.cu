@@ -396,8 +396,11 @@ __device__ __noinline__ void fold_block(const float4* __restrict__ planes, size_
 #ifndef PACKET_TREELET_MINB
 #define PACKET_TREELET_MINB 5
 #endif
+#ifndef PACKET_MINB
+#define PACKET_MINB 0        // 0: ptxas' own choice (48 registers = 5 CTAs of 256 threads per SM, the measured optimum)
+#endif
 template <bool TRI, bool STATS, bool AOV, bool ITEM, bool TREELET = false>
-__global__ void __launch_bounds__(kPacketThreads, TREELET ? PACKET_TREELET_MINB : 0)
+__global__ void __launch_bounds__(kPacketThreads, TREELET ? PACKET_TREELET_MINB : PACKET_MINB)
 k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_prims, const __grid_constant__ CameraBlock cam,
          const __grid_constant__ TileMap tm, int n_work, int spp, uint32_t k0, uint32_t k1, uint32_t sample_offset,
          int resolve, float* __restrict__ d_out, int32_t* __restrict__ d_prim, float* __restrict__ d_t,
