@@ -93,7 +93,7 @@ def _build_to(LIB: str, objdir: str, force: bool, verbose: bool) -> str:
         log += " ".join(cmd) + "\n" + proc.stdout + proc.stderr
         if proc.returncode != 0:
             bad = [(LIB, log, proc.returncode)]
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    with open(os.path.join(HERE, "build.log") if LIB == globals()["LIB"] else LIB + ".log", "w") as f:     # A/B builds keep their own log
         f.write(log)
     if bad:
         raise RuntimeError("nvcc failed:\n" + log[-6000:])
