@@ -235,7 +235,15 @@ int rt_display_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
  * 0 / 1 = its CTA-local wavefront / lock-step form, "tiny_threads" 128 / 256; "treelet" 0..10 = levels of the tree staged in shared
  * memory by the packet / incoherent-ray kernels (0 = off, the measured optimum); "leaf_size" 1..4 = primitives per leaf of builder 0
  * (4 = the reference's rule); "wf_streams" 1 / 2 = waves of a wavefront frame in flight (2: kernel tails overlap); "fold",
- * "wf_rays_per_lane" = measured-and-dropped variants kept for A/B runs. */
+ * "wf_rays_per_lane" = measured-and-dropped variants kept for A/B runs.
+ * "qnodes" = how the incoherent bounces of the wavefront (bounces >= 1, scenes of > 64 primitives) walk the tree; a sum of
+ * 1 = COMPRESSED sibling pairs: a pair in 32 bytes (one 256-bit load instead of two), planes on a 15-bit grid over the root box, rounded
+ * outward, so the closest hits -- and every pixel -- stay those of the full records; 2 = triangle records read as a 32-byte + a 16-byte
+ * part (measured: no gain, kept for A/B runs); 4 = COOPERATIVE leaf step (triangles): the triangles of up to eight leaf-holding lanes are
+ * tested by all 32 lanes of the warp, closest hit folded by a shared-memory atomic min on (distance, primitive) -- the same hit bit for
+ * bit.  -1 (default) = 4, plus 1 while the grid is fine enough for the scene (mean over the leaves of half-area on the grid / half-area
+ * as stored <= "qnodes_area_limit" %, default 115; read-only "qnodes_area_pct", "qnodes_used"); 0 = off.  Instrumented launches
+ * ("stats" 1) always walk the full records, so their counters stay the per-ray walk's. */
 int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);
 int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value);
 int rt_get_stats(rt_ctx* ctx, rt_stats* out);   /* synchronises the device */

@@ -51,6 +51,18 @@ struct rt_ctx {
     float4* d_treelet = nullptr;         // 2^levels - 1 sibling pairs, heap order (k_build_treelet); rebuilt when the tree changes
     int treelet_pairs = 0;
     bool treelet_valid = false;
+    // option "qnodes": compressed copies for the incoherent bounces (k_quantize_pairs / k_split_tris); rebuilt when the tree changes
+    int qmode = -1;                      // -1 auto (bit 0 when the grid is fine enough for the scene), 0 off; forced: bit 0 = 32-byte sibling pairs,
+                                         // bit 1 = split triangle records (measured: no gain on top of bit 0)
+    int qmode_used = 0;                  // what the current tree's launches use
+    int64_t q_area_pct = 0;              // mean over the leaves of (half-area on the grid / half-area as stored), in % (k_quantize_pairs)
+    int q_area_limit = 115;              // auto keeps the compressed pairs up to this
+    uint4* d_qnodes = nullptr;
+    float* d_qgrid = nullptr;
+    float4* d_tri_a = nullptr;
+    float4* d_tri_b = nullptr;
+    int64_t q_pairs = 0, q_tris = 0;     // capacities
+    bool qnodes_valid = false;
     int leaf_size = 4;                   // option "leaf_size": primitives per leaf of builder 0 (4 = the reference's rule)
     int builder = 0;                     // option "builder": what set_scene -> render builds with (0 host median split, 1 device LBVH)
     rt_bvh_node* d_nodes_abi = nullptr;  // device-built tree in ABI layout, until the host mirror is asked for (rt_get_bvh)
@@ -73,6 +85,7 @@ struct rt_ctx {
 
     // options
     int integrator = 0, stats = 0, kernel = -1, refill = 8, leaf_vote = 8, tiny_threads = 256, tiny_mode = 0, wf_rays_per_lane = 0;
+    bool refill_set = false, leaf_vote_set = false;   // set by the caller: also used by the cooperative-leaf launches (whose own optimum is 16 / 7)
     int kernel_used = -1;                    // variant picked by the most recent tracing launch
     // auto choice for multi-bounce renders of tiny scenes (<= 64 primitives): which of the lock-step megakernel
     // (open scenes, short paths: the reference's default scene) and the wavefront (closed scenes, long paths: a
@@ -168,7 +181,7 @@ int cuda_fail(rt_ctx* c, const char* what, cudaError_t e) {
 void free_device_scene(rt_ctx* c) {
     cudaFree(c->d_nodes); cudaFree(c->d_prims); cudaFree(c->d_cam_prims); cudaFree(c->d_nodes_abi); c->d_nodes_abi = nullptr; cudaFree(c->d_slot_prim); cudaFree(c->d_mats);
     c->d_nodes = c->d_prims = c->d_cam_prims = c->d_mats = nullptr; c->d_slot_prim = nullptr;
-    c->device_valid = false; c->cam_table_ok = false; c->treelet_valid = false;
+    c->device_valid = false; c->cam_table_ok = false; c->treelet_valid = false; c->qnodes_valid = false;
 }
 
 // Camera basis exactly as Camera::get_ray builds it (old/raytracer_core copy.h:160-184): forward
@@ -200,12 +213,14 @@ int ensure_bvh(rt_ctx* ctx);
 // RAII around every group of launches that uses context-owned scratch on `stream`: on entry, if the previous such group
 // ran on another stream, make `stream` wait for it; on exit, record the completion event the next group may have to wait on.
 int ensure_treelet(rt_ctx* ctx, cudaStream_t stream);
+int ensure_qnodes(rt_ctx* ctx, cudaStream_t stream);
 struct ScratchOrder {
     rt_ctx* c; cudaStream_t st;
     ScratchOrder(rt_ctx* ctx, void* stream) : c(ctx), st((cudaStream_t)stream) {
         if (!c->scratch_ev) cudaEventCreateWithFlags(&c->scratch_ev, cudaEventDisableTiming);
         if (c->scratch_pending && c->scratch_stream != st) cudaStreamWaitEvent(st, c->scratch_ev, 0);
         ensure_treelet(c, st);                                 // the staged top treelet follows the tree (option "treelet")
+        ensure_qnodes(c, st);                                  // and so do the compressed copies (option "qnodes")
     }
     ~ScratchOrder() {
         if (c->scratch_ev && cudaEventRecord(c->scratch_ev, st) == cudaSuccess) { c->scratch_stream = st; c->scratch_pending = true; }
@@ -376,8 +391,49 @@ int ensure_treelet(rt_ctx* ctx, cudaStream_t stream) {
     return 0;
 }
 
+// (Re)build the compressed pairs / split triangle records for the current tree when option "qnodes" asks for them.
+// Scenes of <= 64 primitives never reach the wavefront's incoherent-bounce kernel and are skipped.
+int ensure_qnodes(rt_ctx* ctx, cudaStream_t stream) {
+    if (ctx->qmode == 0 || ctx->n <= 64 || ctx->n_nodes <= 2 || !ctx->d_nodes || !ctx->device_valid) { ctx->qmode_used = 0; return 0; }
+    if (ctx->qnodes_valid) return 0;
+    ctx->qmode_used = 0;
+    if (!(ctx->root_extent < 0x1p40f)) return 0;
+    const int64_t pairs = (ctx->n_nodes + 1) / 2;
+    if (pairs > ctx->q_pairs) {
+        cudaFree(ctx->d_qnodes); ctx->d_qnodes = nullptr; ctx->q_pairs = 0;
+        CK(cudaMalloc(&ctx->d_qnodes, (size_t)pairs * 32));
+        ctx->q_pairs = pairs;
+    }
+    if (!ctx->d_qgrid) CK(cudaMalloc(&ctx->d_qgrid, 64));              // 6 floats of grid, then (at byte 32) 2 doubles of quality
+    double* d_quality = reinterpret_cast<double*>(ctx->d_qgrid + 8);
+    CK(launch_quantize_pairs(ctx->d_nodes, (int)pairs, ctx->d_qnodes, ctx->d_qgrid, d_quality, stream));
+    double quality[2] = {0.0, 0.0};
+    CK(cudaMemcpyAsync(quality, d_quality, sizeof(quality), cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));                                  // once per tree (build / refit)
+    ctx->q_area_pct = quality[0] > 0.0 ? (int64_t)(100.0 * quality[1] / quality[0] + 0.5) : 100;
+    int mode = ctx->qmode > 0 ? ctx->qmode : (ctx->q_area_pct <= ctx->q_area_limit ? 5 : 4);   // auto: cooperative leaves, pairs when the grid is fine enough
+    if ((mode & 4) && (!ctx->is_tri || ctx->n >= ((int64_t)1 << 25))) mode &= ~4;      // the pair table packs the slot in 25 bits
+    if ((mode & 2) && ctx->is_tri) {
+        if (ctx->n > ctx->q_tris) {
+            cudaFree(ctx->d_tri_a); cudaFree(ctx->d_tri_b); ctx->d_tri_a = ctx->d_tri_b = nullptr; ctx->q_tris = 0;
+            CK(cudaMalloc(&ctx->d_tri_a, (size_t)ctx->n * 32));
+            CK(cudaMalloc(&ctx->d_tri_b, (size_t)ctx->n * 16));
+            ctx->q_tris = ctx->n;
+        }
+        CK(launch_split_tris(ctx->d_prims, (int)ctx->n, ctx->d_tri_a, ctx->d_tri_b, stream));
+        ctx->launches += 1;
+    }
+    ctx->launches += 1;
+    ctx->qmode_used = ctx->is_tri ? mode : (mode & 1);
+    ctx->qnodes_valid = true;
+    return 0;
+}
+
 SceneView scene_view(const rt_ctx* c) {
     SceneView v;
+    const bool q = c->qmode_used != 0 && c->qnodes_valid;
+    v.qnodes = q ? c->d_qnodes : nullptr; v.qgrid = q ? c->d_qgrid : nullptr;
+    v.tri_a = q && (c->qmode_used & 2) ? c->d_tri_a : nullptr; v.tri_b = q && (c->qmode_used & 2) ? c->d_tri_b : nullptr;
     v.treelet = (c->treelet_levels > 0 && c->treelet_valid && c->treelet_pairs > 0) ? c->d_treelet : nullptr;
     v.treelet_two_t = v.treelet ? 2 * c->treelet_pairs : 0;
     v.nodes = c->d_nodes; v.prims = c->d_prims; v.cam_prims = c->d_cam_prims; v.slot_prim = c->d_slot_prim; v.mats = c->d_mats;
@@ -451,6 +507,11 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
     cfg.tiny_threads = c->tiny_threads; cfg.tiny_mode = c->tiny_mode; cfg.wf_rays_per_lane = c->wf_rays_per_lane;
     cfg.refill_below = c->refill;
     cfg.leaf_vote = c->leaf_vote;
+    cfg.qmode = c->qnodes_valid ? c->qmode_used : 0;
+    // the cooperative leaf step serves 8 leaf-holding lanes per pass: measured best with a leaf phase from 7 lanes on and a refill below 16 of 32
+    // traversing lanes (C3 8 spp depth 4: 12.43 ms against 12.75 with the per-lane kernel's 8 / 8)
+    cfg.coop_leaf_vote = c->leaf_vote_set ? c->leaf_vote : 7;
+    cfg.coop_refill = c->refill_set ? c->refill : 16;
     return cfg;
 }
 
@@ -603,6 +664,7 @@ void rt_destroy(rt_ctx* ctx) {
         free_device_scene(ctx);
         free_wave(ctx);
         cudaFree(ctx->d_treelet); cudaFree(ctx->d_fold_cnt);
+        cudaFree(ctx->d_qnodes); cudaFree(ctx->d_qgrid); cudaFree(ctx->d_tri_a); cudaFree(ctx->d_tri_b);
         cudaFree(ctx->d_work_counter); cudaFree(ctx->d_stats); cudaFree(ctx->d_fb); cudaFree(ctx->d_pick); cudaFree(ctx->d_edit); cudaFree(ctx->d_display); cudaFree(ctx->d_planes);
         cudaFree(ctx->d_band_cnt); cudaFree(ctx->d_tile_cnt); cudaFree(ctx->d_chunk_order); cudaFree(ctx->d_chunk_cost);
         if (ctx->h_band_flags) cudaFreeHost(ctx->h_band_flags);
@@ -696,7 +758,7 @@ int rt_update_geometry(rt_ctx* ctx, const float* h_prims, int64_t n) {
     CK(bvh_area(ctx->d_nodes, (int)ctx->n_nodes, d_area, ctx->sm_count, nullptr));
     ctx->launches += 5;
     ctx->refits += 1;
-    ctx->treelet_valid = false;
+    ctx->treelet_valid = false; ctx->qnodes_valid = false;
     double area = 0.0;
     CK(cudaMemcpy(&area, d_area, sizeof(double), cudaMemcpyDeviceToHost));            // synchronises
     ctx->area_pct = ctx->built_area > 0.0 ? (int64_t)(100.0 * area / ctx->built_area) : 100;
@@ -1469,12 +1531,14 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     if (k == "integrator") { if (value != 0 && value != 1) return fail(ctx, "integrator must be 0 (v1) or 1 (v2)"); ctx->integrator = (int)value; }
     else if (k == "stats") ctx->stats = value != 0;
     else if (k == "kernel") { if (value < -1 || value > 5) return fail(ctx, "kernel must be -1 (auto), 0 (k_path), 1 (simple megakernel), 2 (wavefront), 3 (camera-ray packets), 4 (wavefront with packet bounce 0) or 5 (tiny scenes: whole scene in shared memory; other scenes fall back to auto)"); ctx->kernel = (int)value; }
-    else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; }
+    else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; ctx->leaf_vote_set = true; }
     else if (k == "overlap") { if (value < 0 || value > 2) return fail(ctx, "overlap must be 0 (render, then copy), 1 (region flags + DMA copies) or 2 (tile push)"); ctx->overlap = (int)value; }
     else if (k == "refit_limit") { if (value < 0 || value > 100000) return fail(ctx, "refit_limit must be 0 (never rebuild) or a percentage"); ctx->refit_limit = (int)value; }
     else if (k == "builder") { if (value != 0 && value != 1) return fail(ctx, "builder must be 0 (reference median split, host) or 1 (LBVH, device)"); ctx->builder = (int)value; }
     else if (k == "fold") ctx->fold = value != 0;
     else if (k == "treelet") { if (value < 0 || value > 10) return fail(ctx, "treelet must be 0 (off) or 1..10 levels"); ctx->treelet_levels = (int)value; ctx->treelet_valid = false; }
+    else if (k == "qnodes") { if (value < -1 || value > 5) return fail(ctx, "qnodes must be -1 (auto), 0 (off), 1 (compressed sibling pairs), 2 (split triangle records), 3 (both), 4 (cooperative leaf step) or 5 (compressed pairs + cooperative leaf step)"); ctx->qmode = (int)value; ctx->qnodes_valid = false; }
+    else if (k == "qnodes_area_limit") { if (value < 100 || value > 100000) return fail(ctx, "qnodes_area_limit must be a percentage >= 100"); ctx->q_area_limit = (int)value; ctx->qnodes_valid = false; }
     else if (k == "leaf_size") { if (value < 1 || value > 4) return fail(ctx, "leaf_size must be in 1..4"); ctx->leaf_size = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
     else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);
@@ -1482,7 +1546,7 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "wf_rays_per_lane") { if (value < 0 || value > 1024) return fail(ctx, "wf_rays_per_lane must be in 0..1024"); ctx->wf_rays_per_lane = (int)value; }
     else if (k == "tiny_mode") { if (value != 0 && value != 1) return fail(ctx, "tiny_mode must be 0 (CTA-local wavefront) or 1 (lock step)"); ctx->tiny_mode = (int)value; }
     else if (k == "tiny_threads") { if (value != 128 && value != 256) return fail(ctx, "tiny_threads must be 128 or 256"); ctx->tiny_threads = (int)value; }
-    else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; }
+    else if (k == "refill") { if (value < 1 || value > 32) return fail(ctx, "refill must be in 1..32"); ctx->refill = (int)value; ctx->refill_set = true; }
     else return fail(ctx, "rt_set_option: unknown option '" + k + "'");
     return 0;
 }
@@ -1511,6 +1575,10 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "builder") *value = ctx->builder;
     else if (k == "leaf_size") *value = ctx->leaf_size;
     else if (k == "treelet") *value = ctx->treelet_levels;
+    else if (k == "qnodes") *value = ctx->qmode;
+    else if (k == "qnodes_used") *value = ctx->qnodes_valid ? ctx->qmode_used : 0;
+    else if (k == "qnodes_area_pct") *value = ctx->q_area_pct;
+    else if (k == "qnodes_area_limit") *value = ctx->q_area_limit;
     else if (k == "fold") *value = ctx->fold;
     else if (k == "refit_limit") *value = ctx->refit_limit;
     else if (k == "refits") *value = ctx->refits;

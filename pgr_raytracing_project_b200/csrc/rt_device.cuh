@@ -48,6 +48,11 @@ struct SceneView {
     int n_mats;
     int sane_extent;                       // every |coordinate| of the root box < 2^40 (octant slab test usable)
     float bg_r, bg_g, bg_b;
+    // option "qnodes" (incoherent bounces, k_wf_trace): compressed copies of the tree / the triangle records, or nullptr
+    const uint4* __restrict__ qnodes;      // 32 bytes per sibling pair: planes on a 15-bit grid over the root box (k_quantize_pairs)
+    const float* __restrict__ qgrid;       // grid origin xyz, grid extent xyz (written by k_quantize_pairs)
+    const float4* __restrict__ tri_a;      // triangles, leaf order: v0|prim, e1|material (32 bytes, ONE 256-bit load) ...
+    const float4* __restrict__ tri_b;      // ... and e2|0 (16 bytes)
 };
 
 struct Counters { unsigned long long nodes, prims, segments; };
@@ -200,6 +205,68 @@ __device__ __forceinline__ void pair_hit(const PairRec& q, const Ray& r, float t
     const float fl = fminf(fminf(fmaxf(x1.x, x2.x), fmaxf(y1.x, y2.x)), fminf(fmaxf(z1.x, z2.x), thi));
     const float nr = fmaxf(fmaxf(fminf(x1.y, x2.y), fminf(y1.y, y2.y)), fmaxf(fminf(z1.y, z2.y), tlo));
     const float fr = fminf(fminf(fmaxf(x1.y, x2.y), fmaxf(y1.y, y2.y)), fminf(fmaxf(z1.y, z2.y), thi));
+    tl = nl; tr = nr;
+    hl = nl <= fl; hr = nr <= fr;
+}
+
+// ------------------------------------------------------------------------------- compressed sibling pairs (option "qnodes")
+// The per-lane traversal of incoherent rays pays one L1 data-pipe pass per LANE and load instruction (ncu:
+// l1tex__data_pipe_lsu_wavefronts 82 % of peak in k_wf_trace, about 1 wavefront per touched sector), so a sibling pair read as
+// 2 x LDG.256 costs two passes per ray and step.  The compressed copy holds a pair in 32 bytes = ONE 256-bit load:
+//   word 0..2: left child,  per axis  lo16 | hi16 << 16        word 3..5: right child, the same
+//   word 6, 7: the two child codes (as in the full records)
+// A 16-bit plane is 0x8000 | q, q in 0..32767 a cell index of a grid over the (slightly enlarged) root box, rounded OUTWARD
+// by the quantiser (k_quantize_pairs), so that bytes (0x3F, hi byte, lo byte, 0x00) ARE the float f = 1 + q / 32768 and one
+// PRMT (byte permute) decodes a plane; its selector is per lane and picks lo or hi by the sign of the ray's direction, so the
+// decode also replaces the slab test's per-axis min / max.  With A = extent * (1/d) and B = (origin - extent - o) * (1/d)
+// the plane's distance along the ray is fma(f, A, B).  The boxes are conservative (outward rounding + the slack below for
+// the float evaluation), closest hits do not depend on the order or the number of boxes entered (consider()), so the
+// hits are the exact tree's bit for bit; what changes is a few more boxes entered (grid cell = extent / 32768).
+struct QRay { float ax, ay, az, bnx, bny, bnz, bfx, bfy, bfz; unsigned snx, sny, snz; };
+
+__device__ __forceinline__ void ldg_u8(const uint4* __restrict__ p, uint4& a, uint4& b) {
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+constexpr unsigned kQSelLo = 0x7104u, kQSelHi = 0x7324u, kQSelFlip = 0x0220u, kQExp = 0x3F000000u;
+
+// one axis of the ray against the grid: distance of plane f is fma(f, a, b); bn / bf = b minus / plus a slack that covers
+// the rounding of a, b and of the fma itself (each 2^-24 relative to 2|a| + |b|; 2^-21 leaves a factor 4), so that the near
+// value never exceeds and the far value never falls below the exact distance of the (already enlarged) plane
+__device__ __forceinline__ void qray_axis(float g0, float e, float o, float inv, float& a, float& bn, float& bf, unsigned& sn) {
+    a = __fmul_rn(e, inv);
+    const double c = __dsub_rn(__dsub_rn((double)g0, (double)e), (double)o);
+    const float b = __double2float_rn(__dmul_rn(c, (double)inv));
+    const float slack = __fmul_rn(0x1p-21f, __fmaf_rn(2.0f, fabsf(a), fabsf(b)));
+    bn = __fsub_rn(b, slack); bf = __fadd_rn(b, slack);
+    sn = inv < 0.0f ? kQSelHi : kQSelLo;
+}
+__device__ __forceinline__ QRay make_qray(const float* __restrict__ grid, const Ray& r) {
+    QRay q;
+    qray_axis(__ldg(grid + 0), __ldg(grid + 3), r.ox, r.ix, q.ax, q.bnx, q.bfx, q.snx);
+    qray_axis(__ldg(grid + 1), __ldg(grid + 4), r.oy, r.iy, q.ay, q.bny, q.bfy, q.sny);
+    qray_axis(__ldg(grid + 2), __ldg(grid + 5), r.oz, r.iz, q.az, q.bnz, q.bfz, q.snz);
+    return q;
+}
+// (prmt.b32 itself: __byte_perm() masks its selector with 0x7777 first, one more instruction per axis and step)
+__device__ __forceinline__ float qplane(unsigned w, unsigned sel) {
+    unsigned f;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(f) : "r"(w), "r"(kQExp), "r"(sel));
+    return __uint_as_float(f);
+}
+
+// both children of a compressed pair (words w0 = Lx Ly Lz Rx, w1 = Ry Rz Lcode Rcode) against one ray
+__device__ __forceinline__ void pair_hit_q(const uint4& w0, const uint4& w1, const QRay& q, float tlo, float thi,
+                                           bool& hl, bool& hr, float& tl, float& tr) {
+    const unsigned fx = q.snx ^ kQSelFlip, fy = q.sny ^ kQSelFlip, fz = q.snz ^ kQSelFlip;
+    const float2 nx = __ffma2_rn(make_float2(qplane(w0.x, q.snx), qplane(w0.w, q.snx)), make_float2(q.ax, q.ax), make_float2(q.bnx, q.bnx));
+    const float2 ny = __ffma2_rn(make_float2(qplane(w0.y, q.sny), qplane(w1.x, q.sny)), make_float2(q.ay, q.ay), make_float2(q.bny, q.bny));
+    const float2 nz = __ffma2_rn(make_float2(qplane(w0.z, q.snz), qplane(w1.y, q.snz)), make_float2(q.az, q.az), make_float2(q.bnz, q.bnz));
+    const float2 gx = __ffma2_rn(make_float2(qplane(w0.x, fx), qplane(w0.w, fx)), make_float2(q.ax, q.ax), make_float2(q.bfx, q.bfx));
+    const float2 gy = __ffma2_rn(make_float2(qplane(w0.y, fy), qplane(w1.x, fy)), make_float2(q.ay, q.ay), make_float2(q.bfy, q.bfy));
+    const float2 gz = __ffma2_rn(make_float2(qplane(w0.z, fz), qplane(w1.y, fz)), make_float2(q.az, q.az), make_float2(q.bfz, q.bfz));
+    const float nl = fmaxf(fmaxf(nx.x, ny.x), fmaxf(nz.x, tlo)), fl = fminf(fminf(gx.x, gy.x), fminf(gz.x, thi));
+    const float nr = fmaxf(fmaxf(nx.y, ny.y), fmaxf(nz.y, tlo)), fr = fminf(fminf(gx.y, gy.y), fminf(gz.y, thi));
     tl = nl; tr = nr;
     hl = nl <= fl; hr = nr <= fr;
 }
@@ -455,7 +522,6 @@ struct HybridStack {
         else { t = tn[i - D]; c = code[i - D]; }
     }
 };
-
 template <class STACK>
 __device__ __forceinline__ void trav_pop(Trav& tv, const STACK& st) {
     while (tv.sp > 0) {
@@ -494,25 +560,117 @@ __device__ __forceinline__ void trav_begin(const SceneView& sc, const Ray& r, Tr
 // CAM: 0 = no ray of this warp is a camera ray, 1 = all are, 2 = per lane (`cam`).
 constexpr int kNeedPop = (int)0x80000000;   // not a leaf code: would mean first slot 2^28 - 1, count 7
 
-template <bool TRI, bool STATS, int CAM, class STACK, bool TREELET = false>
+// ------------------------------------------------------------------------------- cooperative leaf step (option "qnodes" bit 2)
+// In the leaf phase of trav_run only the lanes that hold a leaf work -- about 10 of 32 in the incoherent bounces -- and each
+// loops over its own <= 4 triangles.  Here the first EIGHT leaf-holding lanes (by lane number; the others keep their leaf for
+// the next phase) hand their <= 4 triangles to the whole warp: owner number j posts (lane, count, first slot) in a per-warp
+// table in shared memory, lane p works for owner p / 4 on its triangle p % 4: it reads the owner's ray from shared memory
+// (every lane keeps a copy of its ray there, k_wf_trace writes it at refill), runs the Moller-Trumbore test of
+// test_tri_mt_records / tri_accept operation by operation, and on a hit folds (distance bits, primitive number, index in the
+// leaf) into the owner's 64-bit best key with one shared-memory atomicMin -- distances are positive floats, so the smallest
+// key is the closest hit, ties to the lower primitive number: consider()'s own rule, hence the same closest hit bit for bit
+// whatever the order.  The owner then applies that one candidate to its closest hit.  One pass of ~24 busy lanes replaces
+// 3-4 passes of ~10.
+struct CoopWarp { float ray[6][32]; uint2 map[8]; unsigned long long best[32]; };   // per warp, shared memory
+
+__device__ __forceinline__ void leaf_phase_coop(const SceneView& sc, Trav& tv, bool is_leaf, int lane, CoopWarp& cw) {
+    const unsigned lb = __ballot_sync(0xffffffffu, is_leaf);
+    const int rank = __popc(lb & ((1u << lane) - 1u));
+    const bool mine = is_leaf && rank < 8;
+    const int code = ~tv.cur;
+    const int cnt = code & 7, first = code >> 3;
+    if (mine) {
+        cw.map[rank] = make_uint2((unsigned)lane | ((unsigned)cnt << 5), (unsigned)first);
+        cw.best[lane] = ~0ull;
+    }
+    __syncwarp();
+    const int n_own = min(__popc(lb), 8), k = lane & 3;
+    if ((lane >> 2) < n_own) {
+        const uint2 m = cw.map[lane >> 2];
+        if (k < (int)(m.x >> 5)) {
+            const int owner = (int)(m.x & 31u), slot = (int)m.y + k;
+            const float ox = cw.ray[0][owner], oy = cw.ray[1][owner], oz = cw.ray[2][owner];
+            const float dx = cw.ray[3][owner], dy = cw.ray[4][owner], dz = cw.ray[5][owner];
+            const float4* p = sc.prims + kTriStride * (size_t)slot;
+            const float4 v0 = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
+            float px, py, pz, qx, qy, qz;
+            cross3(dx, dy, dz, e2.x, e2.y, e2.z, px, py, pz);
+            float det = dot3(e1.x, e1.y, e1.z, px, py, pz);
+            const float sx = __fsub_rn(ox, v0.x), sy = __fsub_rn(oy, v0.y), sz = __fsub_rn(oz, v0.z);
+            float un = dot3(sx, sy, sz, px, py, pz);
+            cross3(sx, sy, sz, e1.x, e1.y, e1.z, qx, qy, qz);
+            float vn = dot3(dx, dy, dz, qx, qy, qz);
+            const float c = dot3(e2.x, e2.y, e2.z, qx, qy, qz);
+            const float sg = det < 0.0f ? -1.0f : 1.0f;
+            det = __fmul_rn(det, sg); un = __fmul_rn(un, sg); vn = __fmul_rn(vn, sg);
+            if (det > 0.0f && un >= 0.0f && vn >= 0.0f && __fadd_rn(un, vn) <= det) {
+                const float t = __fdiv_rn(__fmul_rn(c, sg), det);
+                if (t >= kTMin) {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) |
+                                                   (unsigned long long)(((unsigned)__float_as_int(v0.w) << 2) | (unsigned)k);
+                    atomicMin(&cw.best[owner], key);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (mine) {
+        const unsigned long long key = cw.best[lane];
+        if (key != ~0ull) {
+            const unsigned lo = (unsigned)key;
+            consider(tv.h, __uint_as_float((unsigned)(key >> 32)), (int)(lo >> 2), first + (int)(lo & 3u));
+        }
+        if (cnt > 4) {                                                          // leaves of more than 4 (no builder here makes them)
+            Ray own;
+            own.ox = cw.ray[0][lane]; own.oy = cw.ray[1][lane]; own.oz = cw.ray[2][lane];
+            own.dx = cw.ray[3][lane]; own.dy = cw.ray[4][lane]; own.dz = cw.ray[5][lane];
+            for (int j = 4; j < cnt; ++j) test_tri_mt(sc, first + j, own, tv.h);
+        }
+        tv.cur = kNeedPop;
+    }
+}
+
+// QM (option "qnodes"): bit 0 = internal steps read the compressed pairs (SceneView::qnodes, `qr` = the ray against their grid),
+// bit 1 = triangle records as one 256-bit + one 128-bit load (SceneView::tri_a / tri_b) instead of three 128-bit ones,
+// bit 2 = cooperative leaf step (leaf_phase_coop; triangles, no camera rays; `cw` = this warp's shared-memory area, `lane`).
+template <bool TRI, bool STATS, int CAM, class STACK, bool TREELET = false, int QM = 0>
 __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav& tv, const STACK& st, int min_active,
-                                         int leaf_vote, Counters& cnt, bool cam, const float4* s_tree = nullptr, int two_t = 0) {
+                                         int leaf_vote, Counters& cnt, bool cam, const float4* s_tree = nullptr, int two_t = 0,
+                                         const QRay* qr = nullptr, CoopWarp* cw = nullptr, int lane = 0) {
     for (;;) {
         if (tv.cur == kNeedPop) trav_pop(tv, st);
         const bool is_int = tv.cur >= 0, is_leaf = tv.cur < kDone;
         const int n_int = __popc(__ballot_sync(0xffffffffu, is_int));
         const int n_leaf = __popc(__ballot_sync(0xffffffffu, is_leaf));
         if (n_int + n_leaf < min_active) break;
-        if (n_int == 0 || n_leaf >= leaf_vote) {
+        if (TRI && CAM == 0 && !STATS && (QM & 4) && (n_int == 0 || n_leaf >= leaf_vote)) {
+            leaf_phase_coop(sc, tv, is_leaf, lane, *cw);
+        } else if (n_int == 0 || n_leaf >= leaf_vote) {
             if (is_leaf) {
                 int code = ~tv.cur;
                 int first = code >> 3, count = code & 7;
                 for (int k = 0; k < count; ++k) {
                     if (STATS) cnt.prims += 1;
-                    test_prim<TRI>(sc, first + k, r, tv.h, CAM == 2 ? cam : CAM == 1);
+                    if (TRI && CAM == 0 && (QM & 2)) {
+                        float4 v0, e1;
+                        ldg_node(sc.tri_a + 2 * (size_t)(first + k), v0, e1);
+                        test_tri_mt_records(v0, e1, __ldg(sc.tri_b + first + k), first + k, r, tv.h);
+                    } else test_prim<TRI>(sc, first + k, r, tv.h, CAM == 2 ? cam : CAM == 1);
                 }
                 tv.cur = kNeedPop;
             }
+        } else if (is_int && (QM & 1)) {
+            uint4 w0, w1;
+            ldg_u8(sc.qnodes + tv.cur, w0, w1);                 // pair m = nodes 2m, 2m + 1 = 2 x uint4 at index 2m = cur
+            int lc = (int)w1.z, rc = (int)w1.w;
+            float tl, tr;
+            bool hl, hr;
+            pair_hit_q(w0, w1, *qr, kTMin, tv.h.t, hl, hr, tl, tr);
+            if (hl && hr) {
+                if (tr < tl) { int c = lc; lc = rc; rc = c; float tf = tl; tl = tr; tr = tf; }
+                st.put(tv.sp, rc, tr); ++tv.sp;
+                tv.cur = lc;
+            } else tv.cur = hl ? lc : (hr ? rc : kNeedPop);
         } else if (is_int) {
             PairRec q;
             int lc, rc;

@@ -862,6 +862,83 @@ cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, i
     return cudaGetLastError();
 }
 
+// Option "qnodes": compressed copy of the tree for the incoherent bounces (rt_device.cuh pair_hit_q).  One thread per sibling
+// pair; the grid is the root box enlarged by 1/256 of its extent below and ~1 % above (so that no plane of the tree comes
+// near the ends of the 15-bit range), every thread derives it from node 0 with the same float operations and thread 0
+// publishes it.  lo planes are rounded DOWN and hi planes UP, then moved one more cell outward (covers the rounding of the
+// double division below); 16-bit plane = 0x8000 | cell.
+__device__ __forceinline__ unsigned quantise_axis(float lo, float hi, float g0, float e) {
+    double ul = floor(((double)lo - (double)g0) / (double)e * 32768.0) - 1.0;
+    double uh = ceil(((double)hi - (double)g0) / (double)e * 32768.0) + 1.0;
+    ul = fmin(fmax(ul, 0.0), 32767.0); uh = fmin(fmax(uh, 0.0), 32767.0);          // NaN -> 0
+    return (0x8000u | (unsigned)(int)ul) | ((0x8000u | (unsigned)(int)uh) << 16);
+}
+// quality[0] / quality[1] (zeroed by the launcher): number of LEAF boxes / sum over them of (half-area as the grid renders the
+// box) / (half-area as stored), each ratio capped at 1000 -- the host keeps the compressed copy only while the mean ratio stays
+// close to 1 (a scene whose detail is finer than a grid cell would enter many more leaves).
+__device__ __forceinline__ double qplane_value(unsigned s16, float g0, float e) { return (double)g0 + (double)(s16 & 0x7fffu) * (1.0 / 32768.0) * (double)e; }
+__global__ void __launch_bounds__(256)
+k_quantize_pairs(const float4* __restrict__ nodes, int n_pairs, uint4* __restrict__ out, float* __restrict__ grid, double* __restrict__ quality) {
+    float rlo[3], rhi[3], g0[3], e[3];
+    int rcode;
+    node_read(nodes, 0, rlo, rhi, rcode);
+    for (int c = 0; c < 3; ++c) {
+        const float ext = __fsub_rn(rhi[c], rlo[c]);
+        g0[c] = __fsub_rn(rlo[c], __fmul_rn(ext, 0x1p-8f));
+        e[c] = __fadd_rn(__fmul_rn(ext, 1.015625f), 1e-30f);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int c = 0; c < 3; ++c) { grid[c] = g0[c]; grid[3 + c] = e[c]; }
+    }
+    double area = 0.0, qarea = 0.0;
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n_pairs; m += gridDim.x * blockDim.x) {
+        float lo[3], hi[3];
+        int code[2];
+        unsigned w[6];
+        for (int side = 0; side < 2; ++side) {
+            node_read(nodes, 2 * m + side, lo, hi, code[side]);
+            double d[3], q[3];
+            for (int c = 0; c < 3; ++c) {
+                const unsigned ww = quantise_axis(lo[c], hi[c], g0[c], e[c]);
+                w[3 * side + c] = ww;
+                d[c] = (double)hi[c] - (double)lo[c];
+                q[c] = qplane_value(ww >> 16, g0[c], e[c]) - qplane_value(ww & 0xffffu, g0[c], e[c]);
+            }
+            if (code[side] <= -2 && d[0] >= 0.0 && d[1] >= 0.0 && d[2] >= 0.0) {      // a leaf (the pad record of pair 0 has code 0)
+                const double a0 = d[0] * d[1] + d[1] * d[2] + d[2] * d[0], a1 = q[0] * q[1] + q[1] * q[2] + q[2] * q[0];
+                area += 1.0;
+                qarea += a0 > 0.0 ? fmin(a1 / a0, 1000.0) : 1000.0;
+            }
+        }
+        out[2 * (size_t)m] = make_uint4(w[0], w[1], w[2], w[3]);
+        out[2 * (size_t)m + 1] = make_uint4(w[4], w[5], (unsigned)code[0], (unsigned)code[1]);
+    }
+    for (int o = 16; o > 0; o >>= 1) { area += __shfl_xor_sync(0xffffffffu, area, o); qarea += __shfl_xor_sync(0xffffffffu, qarea, o); }
+    if ((threadIdx.x & 31) == 0 && (area != 0.0 || qarea != 0.0)) { atomicAdd(quality, area); atomicAdd(quality + 1, qarea); }
+}
+// Option "qnodes" bit 1: the 48-byte triangle records as a 32-byte part (v0|prim, e1|material: one 256-bit load) and a 16-byte part (e2|0)
+__global__ void __launch_bounds__(256)
+k_split_tris(const float4* __restrict__ prims, int n, float4* __restrict__ tri_a, float4* __restrict__ tri_b) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        tri_a[2 * (size_t)k] = prims[kTriStride * (size_t)k];
+        tri_a[2 * (size_t)k + 1] = prims[kTriStride * (size_t)k + 1];
+        tri_b[k] = prims[kTriStride * (size_t)k + 2];
+    }
+}
+
+cudaError_t launch_quantize_pairs(const float4* d_nodes, int n_pairs, uint4* d_qnodes, float* d_qgrid, double* d_quality, cudaStream_t stream) {
+    if (n_pairs <= 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(d_quality, 0, 2 * sizeof(double), stream);
+    if (e != cudaSuccess) return e;
+    k_quantize_pairs<<<elementwise_grid(n_pairs), 256, 0, stream>>>(d_nodes, n_pairs, d_qnodes, d_qgrid, d_quality);
+    return cudaGetLastError();
+}
+cudaError_t launch_split_tris(const float4* d_prims, int n, float4* d_tri_a, float4* d_tri_b, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    k_split_tris<<<elementwise_grid(n), 256, 0, stream>>>(d_prims, n, d_tri_a, d_tri_b);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_build_treelet(const float4* d_nodes, int n_pairs, float4* d_treelet, cudaStream_t stream) {
     if (n_pairs <= 0) return cudaSuccess;
     k_build_treelet<<<(n_pairs + 255) / 256, 256, 0, stream>>>(d_nodes, n_pairs, d_treelet);

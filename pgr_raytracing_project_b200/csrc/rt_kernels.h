@@ -91,6 +91,9 @@ struct LaunchCfg {
     int tiny_mode;                           // 0 = CTA-local wavefront with compaction (k_tiny), 1 = lock step per warp (k_tiny_lockstep)
     int refill_below;                        // k_path: leave the traversal loop below this many of 32 lanes
     int leaf_vote;                           // phase voting: leaf step when >= this many lanes hold a leaf
+    int qmode;                               // option "qnodes": k_wf_trace of bounces >= 1 reads compressed pairs (bit 0) / split triangle records (bit 1),
+                                             // runs the cooperative leaf step (bit 2)
+    int coop_leaf_vote, coop_refill;         // leaf_vote / refill_below of the cooperative-leaf launches
 };
 
 // Wavefront state in HBM (allocated by the context, float4 SoA).
@@ -140,6 +143,11 @@ cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, i
 cudaError_t launch_frame_sync(unsigned long long* words, unsigned long long target, cudaStream_t stream);
 // Top `n_pairs` sibling pairs of the tree (heap order) with child codes for shared-memory staging (rt_kernels.cu k_build_treelet).
 cudaError_t launch_build_treelet(const float4* d_nodes, int n_pairs, float4* d_treelet, cudaStream_t stream);
+// Option "qnodes": the tree's sibling pairs compressed to 32 bytes on a 15-bit grid over the root box (d_qgrid: 6 floats), and the
+// triangle records split into a 32-byte and a 16-byte part (rt_device.cuh pair_hit_q, trav_run QM).
+// d_quality[0], [1]: number of leaves, sum of their (half-area on the grid / half-area as stored) (the host's keep-or-drop figure).
+cudaError_t launch_quantize_pairs(const float4* d_nodes, int n_pairs, uint4* d_qnodes, float* d_qgrid, double* d_quality, cudaStream_t stream);
+cudaError_t launch_split_tris(const float4* d_prims, int n, float4* d_tri_a, float4* d_tri_b, cudaStream_t stream);
 // rt_render_tiles_host: this launch's 32x32 tiles of the device frame `fb` stored into the page-locked frame `host` (device
 // alias); the last warp to finish writes `epoch` to *flag (system scope).  cnt: one device word, zeroed here.
 cudaError_t launch_push_tiles(const TileMap& tm, const float* d_fb, float* d_host, unsigned int* d_flag, unsigned int epoch,

@@ -23,6 +23,9 @@ namespace {
 #ifndef B200RT_WF_SMEM_LEVELS
 #define B200RT_WF_SMEM_LEVELS 16
 #endif
+#ifndef B200RT_QTRACE_MIN_CTAS
+#define B200RT_QTRACE_MIN_CTAS 10    // resident CTAs per SM the "qnodes" instances of k_wf_trace are compiled for: a 48-register cap (left alone they take 56-63 and run slower than the full records)
+#endif
 constexpr int kWfSmemLevels = B200RT_WF_SMEM_LEVELS;   // traversal-stack levels of k_wf_trace kept in shared memory (HybridStack)
 
 struct WaveArgs {
@@ -137,8 +140,9 @@ k_wf_packet0(const __grid_constant__ SceneView sc, const float4* __restrict__ ca
 }
 
 // CAM: the rays of this queue are camera rays (bounce 0 of variant 2: triangle test from the per-camera table)
-template <bool TRI, bool STATS, bool CAM, bool TREELET = false>
-__global__ void __launch_bounds__(kThreads)
+// QM: option "qnodes" (bounces >= 1 only): bit 0 = compressed sibling pairs, bit 1 = split triangle records, bit 2 = cooperative leaf step (trav_run)
+template <bool TRI, bool STATS, bool CAM, bool TREELET = false, int QM = 0>
+__global__ void __launch_bounds__(kThreads, QM ? B200RT_QTRACE_MIN_CTAS : 0)
 k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuffers wb, int bounce, int max_depth, int refill_below,
            int leaf_vote, unsigned long long* d_stats, int rays_per_lane) {
     const int lane = threadIdx.x & 31;
@@ -156,6 +160,8 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
     }
     unsigned int* fetch = wb.counters + (max_depth + 1) + bounce;
     __shared__ uint2 s_stack[kWfSmemLevels][kThreads];
+    __shared__ CoopWarp s_coop[(QM & 4) ? kThreads / 32 : 1];   // cooperative leaf step: per-warp ray copies, pair table, best keys
+    CoopWarp& cw = s_coop[(QM & 4) ? (threadIdx.x >> 5) : 0];
     extern __shared__ float4 s_tree[];                         // TREELET: top levels of the tree (SceneView::treelet), option "treelet"
     const int two_t = TREELET ? sc.treelet_two_t : 0;
     if (TREELET) {
@@ -169,6 +175,7 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
     tv.cur = kDone; tv.sp = 0; tv.h.t = kTMax; tv.h.prim = -1; tv.h.slot = -1;
     Counters cnt = {0, 0, 0};
     Ray r = make_ray(0.f, 0.f, 0.f, 0.f, 0.f, 1.f);
+    QRay qr = {};
     int q = -1;
     bool pool_empty = false;
     for (;;) {
@@ -189,6 +196,8 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
                     q = (int)idx;
                     float4 o = __ldg(ray_o + idx), d = __ldg(ray_d + idx);
                     r = make_ray(o.x, o.y, o.z, d.x, d.y, d.z);
+                    if (QM & 1) qr = make_qray(sc.qgrid, r);
+                    if (QM & 4) { cw.ray[0][lane] = o.x; cw.ray[1][lane] = o.y; cw.ray[2][lane] = o.z; cw.ray[3][lane] = d.x; cw.ray[4][lane] = d.y; cw.ray[5][lane] = d.z; }
                     trav_begin<STATS>(sc, r, tv, cnt, two_t);
                 }
             }
@@ -200,8 +209,8 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
             continue;                               // root misses waiting to be published / more to fetch
         }
         int min_active = pool_empty ? 1 : (__popc(act) * refill_below) >> 5;
-        trav_run<TRI, STATS, CAM ? 1 : 0, HybridStack<kWfSmemLevels, kThreads>, TREELET>(sc, r, tv, stack, min_active < 1 ? 1 : min_active, leaf_vote,
-                                                                                          cnt, CAM, s_tree, two_t);
+        trav_run<TRI, STATS, CAM ? 1 : 0, HybridStack<kWfSmemLevels, kThreads>, TREELET, QM>(sc, r, tv, stack, min_active < 1 ? 1 : min_active, leaf_vote,
+                                                                                              cnt, CAM, s_tree, two_t, &qr, &cw, lane);
     }
     if (STATS) flush_stats(d_stats, 0, cnt);
 }
@@ -358,6 +367,16 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
                     int per = 0;
                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kThreads, smem);
                     kern<<<cfg.sm_count * (per < 1 ? 1 : per), kThreads, smem, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, nullptr, cfg.wf_rays_per_lane);
+                } else if (b > 0 && !STATS && cfg.qmode != 0 && sc.qnodes != nullptr) {   // option "qnodes": compressed pairs / split triangle records
+                    int qm = TRI ? cfg.qmode : (cfg.qmode & 1);                  // spheres: the pairs only
+                    if (sc.tri_a == nullptr) qm &= ~2;
+#define B200RT_QTRACE(M) { auto kern = k_wf_trace<TRI, false, false, false, M>; \
+                           kern<<<resident_grid(kern, cfg.sm_count), kThreads, 0, st>>>(sc, wb, b, max_depth, ((M) & 4) ? cfg.coop_refill : cfg.refill_below, \
+                                                                                        ((M) & 4) ? cfg.coop_leaf_vote : cfg.leaf_vote, nullptr, cfg.wf_rays_per_lane); }
+                    if (qm == 1) B200RT_QTRACE(1) else if (qm == 2) B200RT_QTRACE(2) else if (qm == 3) B200RT_QTRACE(3)
+                    else if (TRI && qm == 4) B200RT_QTRACE(4) else if (TRI && qm == 5) B200RT_QTRACE(5) else if (qm == 5) B200RT_QTRACE(1)
+                    else k_wf_trace<TRI, STATS, false><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats, cfg.wf_rays_per_lane);
+#undef B200RT_QTRACE
                 } else if (b > 0)
                     k_wf_trace<TRI, STATS, false><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats, cfg.wf_rays_per_lane);
                 k_wf_shade<TRI, STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(sc, wa, wb, b, d_prim, d_t,
