@@ -92,6 +92,8 @@ int rt_set_background(rt_ctx* ctx, const float rgb[3]);
  * builder 0 = the reference's top-down median split (leaf <= 4, longest axis, median by box
  *             centre), built on the host, deterministic;
  * builder 1 = LBVH built on the device (Morton order), for interactive edits.
+ * builder 2 = binned surface-area heuristic on the host (16 centroid bins per axis; leaves of <= "leaf_size" primitives, cut
+ * further while that is cheaper): a better tree than the reference's rule gives, same pixels (see rt_build_bvh_host_ex).
  * rt_get_bvh / rt_set_bvh let a checker walk the very same tree (nodes may be NULL to query
  * the count).  prim_index has n entries. */
 int rt_build_bvh(rt_ctx* ctx, int builder);
@@ -103,6 +105,12 @@ int rt_set_bvh(rt_ctx* ctx, const rt_bvh_node* h_nodes, int64_t n_nodes, const i
  * at most 2*n + 2 records). */
 int rt_build_bvh_host(const float* h_prims, int is_triangles, int64_t n, rt_bvh_node* h_nodes,
                       int64_t* n_nodes, int32_t* h_prim_index);
+/* The same with a choice of host builder and leaf size: builder 0 = the reference's median split (leaf_size 4 = its rule),
+ * 2 = binned surface-area heuristic -- NOT the reference's tree (cpp_raytracer/raytracer_core.cpp:57-118 knows one rule only):
+ * the same layout and, because closest hits do not depend on the tree, the same hits; fewer nodes entered and primitives
+ * tested per ray.  A tree deeper than the traversal stack (degenerate input) falls back to builder 0.  At most 2*n + 2 records. */
+int rt_build_bvh_host_ex(const float* h_prims, int is_triangles, int64_t n, int builder, int leaf_size,
+                         rt_bvh_node* h_nodes, int64_t* n_nodes, int32_t* h_prim_index);
 
 /* ---- camera: replaces RayTracer::set_camera (old/raytracer_core copy.h:266) + the basis that
  * Camera::get_ray recomputes per ray (old/raytracer_core copy.h:160-184).  aspect <= 0 means
@@ -224,7 +232,7 @@ int rt_display_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
  * bit-identical results; "refill" 1..32 = share (in 32nds)
  * of a warp's traversing lanes below which it leaves the traversal loop to shade / refill (default
  * 8); "leaf_vote" 1..32 = lanes holding a leaf at which the warp runs the leaf step (default 8);
- * "builder" 0/1 = what the implicit build of the first render after a scene upload uses (rt_build_bvh's
+ * "builder" 0/1/2 = what the implicit build of the first render after a scene upload uses (rt_build_bvh's
  * argument; default 0); "schedule" 0/1 = cost-aware work order of the packet kernel (default 1);
  * "overlap" = how rt_render_host moves a camera-ray frame (max_depth 1, 1 spp) to the host: 2 (default) = TILE
  * PUSH, the render kernel itself stores every finished 32x32 tile into h_out (needs page-locked, 16-byte aligned
@@ -233,7 +241,7 @@ int rt_display_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
  * the next renders.  Read-only "host_path" says which way the last rt_render_host took (0 copy, 1 regions, 2 tile push, 3 bands).
  * "kernel" 5 = tiny scenes (<= 64 primitives, max_depth <= 8): the whole scene staged in shared memory (rt_tiny.cu), "tiny_mode"
  * 0 / 1 = its CTA-local wavefront / lock-step form, "tiny_threads" 128 / 256; "treelet" 0..10 = levels of the tree staged in shared
- * memory by the packet / incoherent-ray kernels (0 = off, the measured optimum); "leaf_size" 1..4 = primitives per leaf of builder 0
+ * memory by the packet / incoherent-ray kernels (0 = off, the measured optimum); "sah_cost" = builder 2's cost of a traversal step in tenths of a primitive test (default 30, the measured optimum on the 1M-triangle benchmark scene); "leaf_size" 1..4 = primitives per leaf of builders 0 and 2
  * (4 = the reference's rule); "wf_streams" 1 / 2 = waves of a wavefront frame in flight (2: kernel tails overlap); "fold",
  * "wf_rays_per_lane" = measured-and-dropped variants kept for A/B runs.
  * "qnodes" = how the incoherent bounces of the wavefront (bounces >= 1, scenes of > 64 primitives) walk the tree; a sum of

@@ -14,7 +14,7 @@ SYMBOLS = [
     "rt_set_background", "rt_build_bvh", "rt_get_bvh", "rt_set_bvh", "rt_set_camera", "rt_get_camera_block",
     "rt_trace_primary", "rt_trace_rays", "rt_select_object", "rt_render", "rt_render_tiles", "rt_untile",
     "rt_render_host", "rt_accumulate", "rt_tonemap_u8", "rt_set_option", "rt_get_option", "rt_get_stats",
-    "rt_reset_stats", "rt_build_bvh_host", "rt_render_sum", "rt_resolve", "rt_render_tiles_frame", "rt_frame_alloc",
+    "rt_reset_stats", "rt_build_bvh_host", "rt_build_bvh_host_ex", "rt_render_sum", "rt_resolve", "rt_render_tiles_frame", "rt_frame_alloc",
     "rt_frame_free", "rt_frame_open", "rt_frame_close", "rt_resolve_planes", "rt_display_u8", "rt_update_geometry",
     "rt_update_materials", "rt_frame_sync", "rt_host_register", "rt_host_unregister", "rt_render_tiles_host", "rt_host_wait",
 ]
@@ -69,6 +69,7 @@ def load():
         "rt_get_bvh": (ci, [vp, vp, C.POINTER(i64), ip]),
         "rt_set_bvh": (ci, [vp, vp, i64, ip]),
         "rt_build_bvh_host": (ci, [fp, ci, i64, vp, C.POINTER(i64), ip]),
+        "rt_build_bvh_host_ex": (ci, [fp, ci, i64, ci, ci, vp, C.POINTER(i64), ip]),
         "rt_set_camera": (ci, [vp, dp, dp, dp, C.c_double, C.c_double]),
         "rt_get_camera_block": (ci, [vp, ci, ci, dp]),
         "rt_trace_primary": (ci, [vp, ci, ci, vp, vp, vp]),

@@ -29,8 +29,8 @@ def _dp(a: np.ndarray):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def build_bvh_host(prims: np.ndarray, is_triangles: bool):
-    """Reference-order median-split BVH on the host, no GPU needed (rt_build_bvh_host).
+def build_bvh_host(prims: np.ndarray, is_triangles: bool, builder: int = 0, leaf_size: int = 4):
+    """BVH on the host, no GPU needed (rt_build_bvh_host_ex): builder 0 = the reference-order median split, 2 = binned SAH.
     prims: (n,4) spheres or (n,9) triangles.  -> (nodes[NODE_DTYPE], prim_index int32)."""
     L = _lib.load()
     p = np.ascontiguousarray(prims, dtype=np.float32).reshape(-1, 9 if is_triangles else 4)
@@ -38,7 +38,8 @@ def build_bvh_host(prims: np.ndarray, is_triangles: bool):
     nodes = np.zeros(2 * n + 2, dtype=NODE_DTYPE)
     prim_index = np.zeros(n, dtype=np.int32)
     cnt = C.c_int64(0)
-    if L.rt_build_bvh_host(_fp(p), int(is_triangles), n, nodes.ctypes.data_as(C.c_void_p), C.byref(cnt), _ip(prim_index)) != 0:
+    if L.rt_build_bvh_host_ex(_fp(p), int(is_triangles), n, int(builder), int(leaf_size), nodes.ctypes.data_as(C.c_void_p), C.byref(cnt),
+                              _ip(prim_index)) != 0:
         raise B200RTError(L.rt_last_error(None).decode())
     return nodes[:cnt.value].copy(), prim_index
 

@@ -64,6 +64,7 @@ struct rt_ctx {
     int64_t q_pairs = 0, q_tris = 0;     // capacities
     bool qnodes_valid = false;
     int leaf_size = 4;                   // option "leaf_size": primitives per leaf of builder 0 (4 = the reference's rule)
+    int sah_cost = 30;                   // option "sah_cost": builder 2's cost of a traversal step, in tenths of a primitive test
     int builder = 0;                     // option "builder": what set_scene -> render builds with (0 host median split, 1 device LBVH)
     rt_bvh_node* d_nodes_abi = nullptr;  // device-built tree in ABI layout, until the host mirror is asked for (rt_get_bvh)
     bool host_bvh_stale = false;
@@ -320,6 +321,7 @@ int64_t task_count(const TileMap& tm) { return (int64_t)tm.n_local_tiles * (tm.t
 int ensure_device(rt_ctx* ctx) {
     if (ctx->device_valid) return 0;
     if (int rc = ensure_bvh(ctx)) return rc;
+    if (ctx->device_valid) return 0;                     // the implicit build was the DEVICE builder (option "builder" 1): its arrays are the scene
     free_device_scene(ctx);
     const int64_t n = ctx->n;
     const int64_t n_nodes = (int64_t)ctx->nodes.size();
@@ -866,14 +868,18 @@ static int build_bvh_device(rt_ctx* ctx) {
 int rt_build_bvh(rt_ctx* ctx, int builder) {
     if (!ctx) return 1;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    if (builder != 0 && builder != 1) return fail(ctx, "rt_build_bvh: builder must be 0 (reference median split, host) or 1 (LBVH, device)");
+    if (builder < 0 || builder > 2) return fail(ctx, "rt_build_bvh: builder must be 0 (reference median split, host), 1 (LBVH, device) or 2 (binned SAH, host)");
     ctx->tune_state = 0; ctx->tune_pending = -1;
     if (builder == 1) return build_bvh_device(ctx);
     PrimBoxes boxes;
     if (ctx->is_tri) triangle_boxes(ctx->prim_data.data(), ctx->n, boxes);
     else sphere_boxes(ctx->prim_data.data(), ctx->n, boxes);
-    build_median_split(boxes, ctx->n, ctx->nodes, ctx->prim_index, ctx->leaf_size);
     const char* msg;
+    if (builder == 2) {
+        build_sah(boxes, ctx->n, ctx->nodes, ctx->prim_index, ctx->leaf_size, 0.1f * (float)ctx->sah_cost);
+        if (validate_bvh(ctx->nodes.data(), (int64_t)ctx->nodes.size(), ctx->n, &msg) > kStackDepth - 2) builder = 0;   // degenerate input: the balanced tree
+    }
+    if (builder == 0) build_median_split(boxes, ctx->n, ctx->nodes, ctx->prim_index, ctx->leaf_size);
     ctx->bvh_depth = validate_bvh(ctx->nodes.data(), (int64_t)ctx->nodes.size(), ctx->n, &msg);
     if (ctx->bvh_depth < 0) return fail(ctx, msg);
     if (ctx->bvh_depth > kStackDepth - 2) return fail(ctx, "rt_build_bvh: tree deeper than the traversal stack");
@@ -884,12 +890,24 @@ int rt_build_bvh(rt_ctx* ctx, int builder) {
 
 int rt_build_bvh_host(const float* h_prims, int is_triangles, int64_t n, rt_bvh_node* h_nodes, int64_t* n_nodes,
                       int32_t* h_prim_index) {
+    return rt_build_bvh_host_ex(h_prims, is_triangles, n, 0, 4, h_nodes, n_nodes, h_prim_index);
+}
+
+int rt_build_bvh_host_ex(const float* h_prims, int is_triangles, int64_t n, int builder, int leaf_size, rt_bvh_node* h_nodes,
+                         int64_t* n_nodes, int32_t* h_prim_index) {
     if (n < 0 || (n > 0 && !h_prims) || !n_nodes) return fail(nullptr, "rt_build_bvh_host: bad arguments");
+    if ((builder != 0 && builder != 2) || leaf_size < 1 || leaf_size > 4)
+        return fail(nullptr, "rt_build_bvh_host_ex: builder must be 0 (reference median split) or 2 (binned SAH), leaf_size 1..4");
     PrimBoxes boxes;
     if (is_triangles) triangle_boxes(h_prims, n, boxes); else sphere_boxes(h_prims, n, boxes);
     std::vector<rt_bvh_node> nodes;
     std::vector<int32_t> prim_index;
-    build_median_split(boxes, n, nodes, prim_index);
+    if (builder == 2) {
+        const char* msg;
+        build_sah(boxes, n, nodes, prim_index, leaf_size);
+        if (validate_bvh(nodes.data(), (int64_t)nodes.size(), n, &msg) > kStackDepth - 2) builder = 0;
+    }
+    if (builder == 0) build_median_split(boxes, n, nodes, prim_index, leaf_size);
     *n_nodes = (int64_t)nodes.size();
     if (h_nodes && !nodes.empty()) std::memcpy(h_nodes, nodes.data(), nodes.size() * sizeof(rt_bvh_node));
     if (h_prim_index && n) std::memcpy(h_prim_index, prim_index.data(), (size_t)n * sizeof(int32_t));
@@ -1534,11 +1552,12 @@ int rt_set_option(rt_ctx* ctx, const char* name, int64_t value) {
     else if (k == "leaf_vote") { if (value < 1 || value > 32) return fail(ctx, "leaf_vote must be in 1..32"); ctx->leaf_vote = (int)value; ctx->leaf_vote_set = true; }
     else if (k == "overlap") { if (value < 0 || value > 2) return fail(ctx, "overlap must be 0 (render, then copy), 1 (region flags + DMA copies) or 2 (tile push)"); ctx->overlap = (int)value; }
     else if (k == "refit_limit") { if (value < 0 || value > 100000) return fail(ctx, "refit_limit must be 0 (never rebuild) or a percentage"); ctx->refit_limit = (int)value; }
-    else if (k == "builder") { if (value != 0 && value != 1) return fail(ctx, "builder must be 0 (reference median split, host) or 1 (LBVH, device)"); ctx->builder = (int)value; }
+    else if (k == "builder") { if (value < 0 || value > 2) return fail(ctx, "builder must be 0 (reference median split, host), 1 (LBVH, device) or 2 (binned SAH, host)"); ctx->builder = (int)value; }
     else if (k == "fold") ctx->fold = value != 0;
     else if (k == "treelet") { if (value < 0 || value > 10) return fail(ctx, "treelet must be 0 (off) or 1..10 levels"); ctx->treelet_levels = (int)value; ctx->treelet_valid = false; }
     else if (k == "qnodes") { if (value < -1 || value > 5) return fail(ctx, "qnodes must be -1 (auto), 0 (off), 1 (compressed sibling pairs), 2 (split triangle records), 3 (both), 4 (cooperative leaf step) or 5 (compressed pairs + cooperative leaf step)"); ctx->qmode = (int)value; ctx->qnodes_valid = false; }
     else if (k == "qnodes_area_limit") { if (value < 100 || value > 100000) return fail(ctx, "qnodes_area_limit must be a percentage >= 100"); ctx->q_area_limit = (int)value; ctx->qnodes_valid = false; }
+    else if (k == "sah_cost") { if (value < 0 || value > 1000) return fail(ctx, "sah_cost must be in 0..1000 (tenths of a primitive test)"); ctx->sah_cost = (int)value; }
     else if (k == "leaf_size") { if (value < 1 || value > 4) return fail(ctx, "leaf_size must be in 1..4"); ctx->leaf_size = (int)value; }
     else if (k == "schedule") { ctx->schedule = value != 0; ctx->chunk_key = -1; }
     else if (k == "block_times") ctx->d_block_times = reinterpret_cast<unsigned long long*>((uintptr_t)value);
@@ -1574,6 +1593,7 @@ int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value) {
     else if (k == "n_nodes") *value = ctx->n_nodes;
     else if (k == "builder") *value = ctx->builder;
     else if (k == "leaf_size") *value = ctx->leaf_size;
+    else if (k == "sah_cost") *value = ctx->sah_cost;
     else if (k == "treelet") *value = ctx->treelet_levels;
     else if (k == "qnodes") *value = ctx->qmode;
     else if (k == "qnodes_used") *value = ctx->qnodes_valid ? ctx->qmode_used : 0;

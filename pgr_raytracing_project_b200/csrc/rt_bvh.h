@@ -25,6 +25,13 @@ void triangle_boxes(const float* vertices9, int64_t n, PrimBoxes& out);
 void build_median_split(const PrimBoxes& boxes, int64_t n, std::vector<rt_bvh_node>& nodes,
                         std::vector<int32_t>& prim_index, int leaf_size = 4);   // leaf_size 1..4 (4 = the reference's rule)
 
+// Binned surface-area-heuristic builder (builder 2): NOT the reference's tree -- same layout, same closest hits, fewer
+// steps per ray.  Deterministic for any thread count.
+// trav_cost: cost of one traversal step in primitive tests -- a range of <= leaf_size primitives is cut further while
+// cost(split) + trav_cost * area < area * count.
+void build_sah(const PrimBoxes& boxes, int64_t n, std::vector<rt_bvh_node>& nodes, std::vector<int32_t>& prim_index, int leaf_size = 4,
+               float trav_cost = 3.0f);
+
 // Structural validation of a caller-supplied tree; returns max depth or -1 (msg filled).
 int validate_bvh(const rt_bvh_node* nodes, int64_t n_nodes, int64_t n_prims, const char** msg);
 

@@ -519,3 +519,26 @@ def test_banded_host_frames_and_staged_upload(ctx):
     ctx.build_bvh(0)                                             # the host copy kept by the staged upload feeds a rebuild
     prim2, t2 = [x.cpu().numpy() for x in ctx.trace_primary(W, H)]
     assert np.array_equal(prim2, op) and np.array_equal(t2, ot)
+
+
+def test_implicit_build_with_every_builder(ctx):
+    """Option "builder" picks what the first launch after a scene upload builds with (0 host median split, 1 device LBVH,
+    2 host binned SAH): no explicit rt_build_bvh call, the same pixels from all three.  (Regression: the implicit DEVICE build
+    used to be followed by an upload of the -- empty or stale -- host tree.)"""
+    s = scenes.random_triangles(30_000, seed=41, extent=3.0, size=0.25, cam_z=9.0)
+    W, H = 160, 100
+    cam = s.camera.as_array(W / H)
+    frames = {}
+    try:
+        for builder in (0, 1, 2, 1):
+            ctx.set_option("builder", builder)
+            ctx.set_scene(s, build_bvh=False)
+            ctx.set_camera_array(cam)
+            a = ctx.render(W, H, 1, 1, seed=2).cpu().numpy()
+            b = ctx.render(W, H, 2, 4, seed=2).cpu().numpy()
+            frames.setdefault("a", a); frames.setdefault("b", b)
+            assert np.array_equal(a, frames["a"]) and np.array_equal(b, frames["b"]), builder
+            nodes, prim_index = ctx.get_bvh()
+            assert sorted(prim_index.tolist()) == list(range(s.n_prims)) and len(nodes) == ctx.get_option("n_nodes")
+    finally:
+        ctx.set_option("builder", 0)

@@ -98,7 +98,7 @@ def test_qnodes_follow_refit_and_rebuild(ctx):
         ctx.set_option("builder", 1)                        # device LBVH: another tree, the same pixels
         s2 = scenes.random_triangles(20000, seed=9, extent=3.0, size=0.3, cam_z=9.0)
         s2.vertices = moved.reshape(s.vertices.shape)
-        ctx.set_scene(s2)
+        ctx.set_scene(s2, build_bvh=False)                  # the first launch builds, with option "builder"
         ctx.set_option("qnodes", 5)
         img2 = ctx.render(W, H, spp, depth, seed=5).cpu().numpy()
         assert np.array_equal(img2, ref)
