@@ -410,9 +410,8 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
     // planes != nullptr: ITEM MODE for multi-sample frames -- the work item is (block, sample) instead of a block
     // with a sample loop inside: item = block * plane_batch + sb, sample plane_sample0 + sb, radiance written to
     // planes[sb][block * 32 + lane]; k_plane_accumulate then adds the planes in sample order (same bits as the
-    // loop) and resolves.  Items of one block are neighbours in the item order, so the 8 warps of a CTA trace
-    // the same block's samples side by side (shared L1 lines), and a frame of few blocks and many samples (one
-    // rank's tiles of a multi-GPU frame) still splits into enough items to balance.
+    // loop) and resolves.  A frame of few blocks and many samples (one rank's tiles of a multi-GPU frame) thus
+    // splits into enough items to balance; the item ORDER is described where items are decoded below.
     __shared__ uint2 s_stack[kPacketThreads / 32][kStackDepth];
     __shared__ unsigned s_word;
     extern __shared__ float4 s_tree[];                         // TREELET: the top levels of the tree (SceneView::treelet)
@@ -434,8 +433,22 @@ k_packet(const __grid_constant__ SceneView sc, const float4* __restrict__ cam_pr
         const int item = chunk_next_block(&s_word, counter, n_chunks, sched.order, lane);
         if (item < 0) break;
         if (item >= n_items) continue;
+#ifndef B200RT_ITEM_SAMPLES_ADJACENT
+        // Item order: a chunk (8 consecutive items = what the 8 warps of a CTA take together) is 8 DIFFERENT neighbouring blocks at
+        // one sample, the next chunk the same blocks at the next sample.  With the samples of ONE block side by side (the first
+        // form, -DB200RT_ITEM_SAMPLES_ADJACENT) the 8 warps walk the same nodes at the same time and stall TOGETHER on every line
+        // the first of them misses (long-scoreboard 5.1 -> 7.7 cycles per issue, ncu): one rank's share of an 8-GPU frame 0.385 ->
+        // 0.348 ms, the 8-spp frame on one GPU 2.83 -> 2.51 ms (profiles/r02z_exp_item_order.txt).  Same planes, same pixels.
+        int w = item, item_sb = 0;
+        if (item_mode) {
+            const int per_group = kChunk * plane_batch, g = item / per_group, r = item - g * per_group;
+            const int gs = min(kChunk, n_work - g * kChunk);
+            w = g * kChunk + r % gs; item_sb = r / gs;
+        }
+#else
         const int w = item_mode ? item / plane_batch : item;
         const int item_sb = item_mode ? item - w * plane_batch : 0;
+#endif
         PixelWork p = decode_work(tm, w, lane);
         const uint32_t pixel = (uint32_t)(p.j * tm.width + p.i);
         float sr = 0.0f, sg = 0.0f, sb = 0.0f;
