@@ -134,6 +134,14 @@ __device__ __forceinline__ Ray camera_ray(const CameraBlock& c, int i, int j, fl
 // ------------------------------------------------------------------------------- intersection
 struct Hit { float t; int prim; int slot; };
 
+// explicit shared-memory accesses through a 32-bit shared-window address (HybridStackA, leaf_phase_coop)
+__device__ __forceinline__ void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_v2(unsigned a, unsigned x, unsigned y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(a), "r"(x), "r"(y) : "memory"); }
+__device__ __forceinline__ uint2 lds_v2(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void reds_min_u64(unsigned a, unsigned long long v) { asm volatile("red.shared.min.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
+
+
 // A sibling pair (64 bytes, 64-byte aligned) as TWO 256-bit loads (LDG.E.256.CONSTANT, sm_100: ld.global.nc.v8.f32)
 // instead of four 128-bit ones.  The per-lane traversal of incoherent rays is bound by the L1TEX tag stage: every
 // load instruction costs one pass per DISTINCT 128-byte line among the lanes, however many bytes each lane takes
@@ -572,27 +580,37 @@ constexpr int kNeedPop = (int)0x80000000;   // not a leaf code: would mean first
 // whatever the order.  The owner then applies that one candidate to its closest hit.  One pass of ~24 busy lanes replaces
 // 3-4 passes of ~10.
 struct CoopWarp { float ray[6][32]; uint2 map[8]; unsigned long long best[32]; };   // per warp, shared memory
+// The area is addressed through ONE register, its 32-bit shared-memory address (`sa`, kept live by k_wf_trace), with explicit
+// ld / st / red.shared: through a generic pointer the compiler re-derives the address from %tid and the shared window at every
+// use (3 x 8 instructions per leaf phase at 32 lanes, two of them S2R).
+constexpr unsigned kCoopMap = 768u, kCoopBest = 832u;                                // byte offsets of map / best in CoopWarp
+__device__ __forceinline__ void coop_store_ray(unsigned sa, int lane, const float4& o, const float4& d) {
+    const unsigned a = sa + 4u * (unsigned)lane;
+    sts_f32(a, o.x); sts_f32(a + 128u, o.y); sts_f32(a + 256u, o.z); sts_f32(a + 384u, d.x); sts_f32(a + 512u, d.y); sts_f32(a + 640u, d.z);
+}
 
-__device__ __forceinline__ void leaf_phase_coop(const SceneView& sc, Trav& tv, bool is_leaf, int lane, CoopWarp& cw) {
+__device__ __forceinline__ void leaf_phase_coop(const SceneView& sc, Trav& tv, bool is_leaf, int lane, unsigned sa) {
     const unsigned lb = __ballot_sync(0xffffffffu, is_leaf);
     const int rank = __popc(lb & ((1u << lane) - 1u));
     const bool mine = is_leaf && rank < 8;
     const int code = ~tv.cur;
     const int cnt = code & 7, first = code >> 3;
     if (mine) {
-        cw.map[rank] = make_uint2((unsigned)lane | ((unsigned)cnt << 5), (unsigned)first);
-        cw.best[lane] = ~0ull;
+        sts_v2(sa + kCoopMap + 8u * (unsigned)rank, (unsigned)lane | ((unsigned)cnt << 5), (unsigned)first);
+        sts_v2(sa + kCoopBest + 8u * (unsigned)lane, 0xffffffffu, 0xffffffffu);
     }
     __syncwarp();
     const int n_own = min(__popc(lb), 8), k = lane & 3;
     if ((lane >> 2) < n_own) {
-        const uint2 m = cw.map[lane >> 2];
+        const uint2 m = lds_v2(sa + kCoopMap + 8u * (unsigned)(lane >> 2));
         if (k < (int)(m.x >> 5)) {
-            const int owner = (int)(m.x & 31u), slot = (int)m.y + k;
-            const float ox = cw.ray[0][owner], oy = cw.ray[1][owner], oz = cw.ray[2][owner];
-            const float dx = cw.ray[3][owner], dy = cw.ray[4][owner], dz = cw.ray[5][owner];
+            const unsigned owner = m.x & 31u;
+            const int slot = (int)m.y + k;
             const float4* p = sc.prims + kTriStride * (size_t)slot;
             const float4 v0 = __ldg(p), e1 = __ldg(p + 1), e2 = __ldg(p + 2);
+            const unsigned ra = sa + 4u * owner;
+            const float ox = lds_f32(ra), oy = lds_f32(ra + 128u), oz = lds_f32(ra + 256u);
+            const float dx = lds_f32(ra + 384u), dy = lds_f32(ra + 512u), dz = lds_f32(ra + 640u);
             float px, py, pz, qx, qy, qz;
             cross3(dx, dy, dz, e2.x, e2.y, e2.z, px, py, pz);
             float det = dot3(e1.x, e1.y, e1.z, px, py, pz);
@@ -605,25 +623,22 @@ __device__ __forceinline__ void leaf_phase_coop(const SceneView& sc, Trav& tv, b
             det = __fmul_rn(det, sg); un = __fmul_rn(un, sg); vn = __fmul_rn(vn, sg);
             if (det > 0.0f && un >= 0.0f && vn >= 0.0f && __fadd_rn(un, vn) <= det) {
                 const float t = __fdiv_rn(__fmul_rn(c, sg), det);
-                if (t >= kTMin) {
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) |
-                                                   (unsigned long long)(((unsigned)__float_as_int(v0.w) << 2) | (unsigned)k);
-                    atomicMin(&cw.best[owner], key);
-                }
+                if (t >= kTMin)
+                    reds_min_u64(sa + kCoopBest + 8u * owner, ((unsigned long long)__float_as_uint(t) << 32) |
+                                                              (unsigned long long)(((unsigned)__float_as_int(v0.w) << 2) | (unsigned)k));
             }
         }
     }
     __syncwarp();
     if (mine) {
-        const unsigned long long key = cw.best[lane];
-        if (key != ~0ull) {
-            const unsigned lo = (unsigned)key;
-            consider(tv.h, __uint_as_float((unsigned)(key >> 32)), (int)(lo >> 2), first + (int)(lo & 3u));
-        }
+        const uint2 key = lds_v2(sa + kCoopBest + 8u * (unsigned)lane);                 // .x = primitive << 2 | index in leaf, .y = distance bits
+        if ((key.x & key.y) != 0xffffffffu)
+            consider(tv.h, __uint_as_float(key.y), (int)(key.x >> 2), first + (int)(key.x & 3u));
         if (cnt > 4) {                                                          // leaves of more than 4 (no builder here makes them)
+            const unsigned a = sa + 4u * (unsigned)lane;
             Ray own;
-            own.ox = cw.ray[0][lane]; own.oy = cw.ray[1][lane]; own.oz = cw.ray[2][lane];
-            own.dx = cw.ray[3][lane]; own.dy = cw.ray[4][lane]; own.dz = cw.ray[5][lane];
+            own.ox = lds_f32(a); own.oy = lds_f32(a + 128u); own.oz = lds_f32(a + 256u);
+            own.dx = lds_f32(a + 384u); own.dy = lds_f32(a + 512u); own.dz = lds_f32(a + 640u);
             for (int j = 4; j < cnt; ++j) test_tri_mt(sc, first + j, own, tv.h);
         }
         tv.cur = kNeedPop;
@@ -632,11 +647,11 @@ __device__ __forceinline__ void leaf_phase_coop(const SceneView& sc, Trav& tv, b
 
 // QM (option "qnodes"): bit 0 = internal steps read the compressed pairs (SceneView::qnodes, `qr` = the ray against their grid),
 // bit 1 = triangle records as one 256-bit + one 128-bit load (SceneView::tri_a / tri_b) instead of three 128-bit ones,
-// bit 2 = cooperative leaf step (leaf_phase_coop; triangles, no camera rays; `cw` = this warp's shared-memory area, `lane`).
+// bit 2 = cooperative leaf step (leaf_phase_coop; triangles, no camera rays; `coop_sa` = shared-memory address of this warp's CoopWarp, `lane`).
 template <bool TRI, bool STATS, int CAM, class STACK, bool TREELET = false, int QM = 0>
 __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav& tv, const STACK& st, int min_active,
                                          int leaf_vote, Counters& cnt, bool cam, const float4* s_tree = nullptr, int two_t = 0,
-                                         const QRay* qr = nullptr, CoopWarp* cw = nullptr, int lane = 0) {
+                                         const QRay* qr = nullptr, unsigned coop_sa = 0u, int lane = 0) {
     for (;;) {
         if (tv.cur == kNeedPop) trav_pop(tv, st);
         const bool is_int = tv.cur >= 0, is_leaf = tv.cur < kDone;
@@ -644,7 +659,7 @@ __device__ __forceinline__ void trav_run(const SceneView& sc, const Ray& r, Trav
         const int n_leaf = __popc(__ballot_sync(0xffffffffu, is_leaf));
         if (n_int + n_leaf < min_active) break;
         if (TRI && CAM == 0 && !STATS && (QM & 4) && (n_int == 0 || n_leaf >= leaf_vote)) {
-            leaf_phase_coop(sc, tv, is_leaf, lane, *cw);
+            leaf_phase_coop(sc, tv, is_leaf, lane, coop_sa);
         } else if (n_int == 0 || n_leaf >= leaf_vote) {
             if (is_leaf) {
                 int code = ~tv.cur;

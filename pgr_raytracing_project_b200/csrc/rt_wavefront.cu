@@ -161,7 +161,8 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
     unsigned int* fetch = wb.counters + (max_depth + 1) + bounce;
     __shared__ uint2 s_stack[kWfSmemLevels][kThreads];
     __shared__ CoopWarp s_coop[(QM & 4) ? kThreads / 32 : 1];   // cooperative leaf step: per-warp ray copies, pair table, best keys
-    CoopWarp& cw = s_coop[(QM & 4) ? (threadIdx.x >> 5) : 0];
+    unsigned coop_sa = (unsigned)__cvta_generic_to_shared(&s_coop[(QM & 4) ? (threadIdx.x >> 5) : 0]);
+    if (QM & 4) asm volatile("" : "+r"(coop_sa));            // one live register instead of re-deriving the address at every use
     extern __shared__ float4 s_tree[];                         // TREELET: top levels of the tree (SceneView::treelet), option "treelet"
     const int two_t = TREELET ? sc.treelet_two_t : 0;
     if (TREELET) {
@@ -170,7 +171,8 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
     }
     int stack_code[kStackDepth - kWfSmemLevels];
     float stack_tn[kStackDepth - kWfSmemLevels];
-    const HybridStack<kWfSmemLevels, kThreads> stack{&s_stack[0][threadIdx.x], stack_code, stack_tn};
+const HybridStack<kWfSmemLevels, kThreads> stack{&s_stack[0][threadIdx.x], stack_code, stack_tn};
+    typedef HybridStack<kWfSmemLevels, kThreads> StackT;
     Trav tv;
     tv.cur = kDone; tv.sp = 0; tv.h.t = kTMax; tv.h.prim = -1; tv.h.slot = -1;
     Counters cnt = {0, 0, 0};
@@ -197,7 +199,7 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
                     float4 o = __ldg(ray_o + idx), d = __ldg(ray_d + idx);
                     r = make_ray(o.x, o.y, o.z, d.x, d.y, d.z);
                     if (QM & 1) qr = make_qray(sc.qgrid, r);
-                    if (QM & 4) { cw.ray[0][lane] = o.x; cw.ray[1][lane] = o.y; cw.ray[2][lane] = o.z; cw.ray[3][lane] = d.x; cw.ray[4][lane] = d.y; cw.ray[5][lane] = d.z; }
+                    if (QM & 4) coop_store_ray(coop_sa, lane, o, d);
                     trav_begin<STATS>(sc, r, tv, cnt, two_t);
                 }
             }
@@ -209,8 +211,8 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
             continue;                               // root misses waiting to be published / more to fetch
         }
         int min_active = pool_empty ? 1 : (__popc(act) * refill_below) >> 5;
-        trav_run<TRI, STATS, CAM ? 1 : 0, HybridStack<kWfSmemLevels, kThreads>, TREELET, QM>(sc, r, tv, stack, min_active < 1 ? 1 : min_active, leaf_vote,
-                                                                                              cnt, CAM, s_tree, two_t, &qr, &cw, lane);
+        trav_run<TRI, STATS, CAM ? 1 : 0, StackT, TREELET, QM>(sc, r, tv, stack, min_active < 1 ? 1 : min_active, leaf_vote,
+                                                                                              cnt, CAM, s_tree, two_t, &qr, coop_sa, lane);
     }
     if (STATS) flush_stats(d_stats, 0, cnt);
 }
