@@ -86,7 +86,7 @@ struct rt_ctx {
 
     // options
     int integrator = 0, stats = 0, kernel = -1, refill = 8, leaf_vote = 8, tiny_threads = 256, tiny_mode = 0, wf_rays_per_lane = 0;
-    bool refill_set = false, leaf_vote_set = false;   // set by the caller: also used by the cooperative-leaf launches (whose own optimum is 16 / 7)
+    bool refill_set = false, leaf_vote_set = false;   // set by the caller: also used by the cooperative-leaf launches (whose own optimum is 24 / 7)
     int kernel_used = -1;                    // variant picked by the most recent tracing launch
     // auto choice for multi-bounce renders of tiny scenes (<= 64 primitives): which of the lock-step megakernel
     // (open scenes, short paths: the reference's default scene) and the wavefront (closed scenes, long paths: a
@@ -510,10 +510,11 @@ LaunchCfg launch_cfg(rt_ctx* c, void* stream, int max_depth = 1, int variant = -
     cfg.refill_below = c->refill;
     cfg.leaf_vote = c->leaf_vote;
     cfg.qmode = c->qnodes_valid ? c->qmode_used : 0;
-    // the cooperative leaf step serves 8 leaf-holding lanes per pass: measured best with a leaf phase from 7 lanes on and a refill below 16 of 32
-    // traversing lanes (C3 8 spp depth 4: 12.43 ms against 12.75 with the per-lane kernel's 8 / 8)
+    // the cooperative leaf step serves 8 leaf-holding lanes per pass: measured best with a leaf phase from 7 lanes on and a refill below 24 of 32
+    // traversing lanes -- idle lanes still work in the leaf passes, so refilling early costs little (C3 8 spp depth 4: 12.75 ms with the
+    // per-lane kernel's 8 / 8, 12.43 with 7 / 16, 12.22 with 7 / 24, 12.55 with 7 / 28; profiles/r02y_exp_qnodes_coop.txt)
     cfg.coop_leaf_vote = c->leaf_vote_set ? c->leaf_vote : 7;
-    cfg.coop_refill = c->refill_set ? c->refill : 16;
+    cfg.coop_refill = c->refill_set ? c->refill : 24;
     return cfg;
 }
 
