@@ -171,8 +171,8 @@ k_wf_trace(const __grid_constant__ SceneView sc, const __grid_constant__ WaveBuf
     }
     int stack_code[kStackDepth - kWfSmemLevels];
     float stack_tn[kStackDepth - kWfSmemLevels];
-const HybridStack<kWfSmemLevels, kThreads> stack{&s_stack[0][threadIdx.x], stack_code, stack_tn};
     typedef HybridStack<kWfSmemLevels, kThreads> StackT;
+    const StackT stack{&s_stack[0][threadIdx.x], stack_code, stack_tn};
     Trav tv;
     tv.cur = kDone; tv.sp = 0; tv.h.t = kTMax; tv.h.prim = -1; tv.h.slot = -1;
     Counters cnt = {0, 0, 0};
@@ -300,6 +300,35 @@ int grid_for(int64_t n, int threads, int sm_count, int per_sm) {
     return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
+// Option "qnodes": the k_wf_trace instance for the mode the context settled on (LaunchCfg::qmode; rt_api.cu ensure_qnodes).
+// false = no such instance applies (the caller launches the full-record kernel).
+template <bool TRI, int M>
+void launch_qtrace_mode(const SceneView& sc, const WaveBuffers& wb, int b, int max_depth, const LaunchCfg& cfg, cudaStream_t st) {
+    auto kern = k_wf_trace<TRI, false, false, false, M>;
+    static const int per_sm = [] {
+        int n = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_wf_trace<TRI, false, false, false, M>, kThreads, 0);
+        return n < 1 ? 1 : n;
+    }();
+    kern<<<cfg.sm_count * per_sm, kThreads, 0, st>>>(sc, wb, b, max_depth, (M & 4) ? cfg.coop_refill : cfg.refill_below,
+                                                   (M & 4) ? cfg.coop_leaf_vote : cfg.leaf_vote, nullptr, cfg.wf_rays_per_lane);
+}
+template <bool TRI>
+bool launch_qtrace(const SceneView& sc, const WaveBuffers& wb, int b, int max_depth, const LaunchCfg& cfg, cudaStream_t st) {
+    if (cfg.qmode == 0 || sc.qnodes == nullptr) return false;
+    int qm = TRI ? cfg.qmode : (cfg.qmode & 1);              // spheres: the pairs only
+    if (sc.tri_a == nullptr) qm &= ~2;
+    if (qm == 1) launch_qtrace_mode<TRI, 1>(sc, wb, b, max_depth, cfg, st);
+    else if constexpr (TRI) {
+        if (qm == 2) launch_qtrace_mode<true, 2>(sc, wb, b, max_depth, cfg, st);
+        else if (qm == 3) launch_qtrace_mode<true, 3>(sc, wb, b, max_depth, cfg, st);
+        else if (qm == 4) launch_qtrace_mode<true, 4>(sc, wb, b, max_depth, cfg, st);
+        else if (qm == 5) launch_qtrace_mode<true, 5>(sc, wb, b, max_depth, cfg, st);
+        else return false;
+    } else return false;
+    return true;
+}
+
 template <bool TRI, bool STATS, bool AOV>
 cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const TileMap& tm, int spp, int max_depth,
                           int integrator, uint64_t seed, uint32_t sample_offset, int resolve, float* d_out,
@@ -369,16 +398,7 @@ cudaError_t run_wavefront(const SceneView& sc, const CameraBlock& cam, const Til
                     int per = 0;
                     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, kThreads, smem);
                     kern<<<cfg.sm_count * (per < 1 ? 1 : per), kThreads, smem, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, nullptr, cfg.wf_rays_per_lane);
-                } else if (b > 0 && !STATS && cfg.qmode != 0 && sc.qnodes != nullptr) {   // option "qnodes": compressed pairs / split triangle records
-                    int qm = TRI ? cfg.qmode : (cfg.qmode & 1);                  // spheres: the pairs only
-                    if (sc.tri_a == nullptr) qm &= ~2;
-#define B200RT_QTRACE(M) { auto kern = k_wf_trace<TRI, false, false, false, M>; \
-                           kern<<<resident_grid(kern, cfg.sm_count), kThreads, 0, st>>>(sc, wb, b, max_depth, ((M) & 4) ? cfg.coop_refill : cfg.refill_below, \
-                                                                                        ((M) & 4) ? cfg.coop_leaf_vote : cfg.leaf_vote, nullptr, cfg.wf_rays_per_lane); }
-                    if (qm == 1) B200RT_QTRACE(1) else if (qm == 2) B200RT_QTRACE(2) else if (qm == 3) B200RT_QTRACE(3)
-                    else if (TRI && qm == 4) B200RT_QTRACE(4) else if (TRI && qm == 5) B200RT_QTRACE(5) else if (qm == 5) B200RT_QTRACE(1)
-                    else k_wf_trace<TRI, STATS, false><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats, cfg.wf_rays_per_lane);
-#undef B200RT_QTRACE
+                } else if (b > 0 && !STATS && launch_qtrace<TRI>(sc, wb, b, max_depth, cfg, st)) {   // option "qnodes": compressed pairs / cooperative leaves
                 } else if (b > 0)
                     k_wf_trace<TRI, STATS, false><<<trace_grid, kThreads, 0, st>>>(sc, wb, b, max_depth, cfg.refill_below, cfg.leaf_vote, cfg.d_stats, cfg.wf_rays_per_lane);
                 k_wf_shade<TRI, STATS, AOV><<<grid_for(wa.n_paths, 256, cfg.sm_count, 8), 256, 0, st>>>(sc, wa, wb, b, d_prim, d_t,
