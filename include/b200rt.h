@@ -250,7 +250,8 @@ int rt_display_u8(rt_ctx* ctx, const float* d_accum, uint8_t* d_rgb8, int64_t n_
  * part (measured: no gain, kept for A/B runs); 4 = COOPERATIVE leaf step (triangles): the triangles of up to eight leaf-holding lanes are
  * tested by all 32 lanes of the warp, closest hit folded by a shared-memory atomic min on (distance, primitive) -- the same hit bit for
  * bit.  -1 (default) = 4, plus 1 while the grid is fine enough for the scene (mean over the leaves of half-area on the grid / half-area
- * as stored <= "qnodes_area_limit" %, default 115; read-only "qnodes_area_pct", "qnodes_used"); 0 = off.  Instrumented launches
+ * as stored <= "qnodes_area_limit" %, default 115; read-only "qnodes_area_pct", "qnodes_used"); 0 = off.  A tree with a box outside the root box
+ * (possible only with rt_set_bvh) never uses the compressed pairs ("qnodes_area_pct" reads -1).  Instrumented launches
  * ("stats" 1) always walk the full records, so their counters stay the per-ray walk's. */
 int rt_set_option(rt_ctx* ctx, const char* name, int64_t value);
 int rt_get_option(rt_ctx* ctx, const char* name, int64_t* value);

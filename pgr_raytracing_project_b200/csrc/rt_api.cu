@@ -406,14 +406,15 @@ int ensure_qnodes(rt_ctx* ctx, cudaStream_t stream) {
         CK(cudaMalloc(&ctx->d_qnodes, (size_t)pairs * 32));
         ctx->q_pairs = pairs;
     }
-    if (!ctx->d_qgrid) CK(cudaMalloc(&ctx->d_qgrid, 64));              // 6 floats of grid, then (at byte 32) 2 doubles of quality
+    if (!ctx->d_qgrid) CK(cudaMalloc(&ctx->d_qgrid, 64));              // 6 floats of grid, then (at byte 32) 3 doubles of quality
     double* d_quality = reinterpret_cast<double*>(ctx->d_qgrid + 8);
     CK(launch_quantize_pairs(ctx->d_nodes, (int)pairs, ctx->d_qnodes, ctx->d_qgrid, d_quality, stream));
-    double quality[2] = {0.0, 0.0};
+    double quality[3] = {0.0, 0.0, 0.0};
     CK(cudaMemcpyAsync(quality, d_quality, sizeof(quality), cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));                                  // once per tree (build / refit)
     ctx->q_area_pct = quality[0] > 0.0 ? (int64_t)(100.0 * quality[1] / quality[0] + 0.5) : 100;
     int mode = ctx->qmode > 0 ? ctx->qmode : (ctx->q_area_pct <= ctx->q_area_limit ? 5 : 4);   // auto: cooperative leaves, pairs when the grid is fine enough
+    if (quality[2] != 0.0) { mode &= ~1; ctx->q_area_pct = -1; }                        // a box outside the root box (caller-supplied tree): full records only
     if ((mode & 4) && (!ctx->is_tri || ctx->n >= ((int64_t)1 << 25))) mode &= ~4;      // the pair table packs the slot in 25 bits
     if ((mode & 2) && ctx->is_tri) {
         if (ctx->n > ctx->q_tris) {

@@ -880,15 +880,19 @@ cudaError_t launch_accumulate(const float* d_batch, float* d_accum, int64_t n, i
 // near the ends of the 15-bit range), every thread derives it from node 0 with the same float operations and thread 0
 // publishes it.  lo planes are rounded DOWN and hi planes UP, then moved one more cell outward (covers the rounding of the
 // double division below); 16-bit plane = 0x8000 | cell.
-__device__ __forceinline__ unsigned quantise_axis(float lo, float hi, float g0, float e) {
+// out_of_range: a plane that does not fit the grid (a caller-supplied tree whose child sticks out of the root box, NaN boxes):
+// clamping it would SHRINK the box, so the host drops the compressed copy for such a tree.
+__device__ __forceinline__ unsigned quantise_axis(float lo, float hi, float g0, float e, bool& out_of_range) {
     double ul = floor(((double)lo - (double)g0) / (double)e * 32768.0) - 1.0;
     double uh = ceil(((double)hi - (double)g0) / (double)e * 32768.0) + 1.0;
+    if (!(ul >= 0.0 && uh <= 32767.0)) out_of_range = true;                       // (NaN compares false)
     ul = fmin(fmax(ul, 0.0), 32767.0); uh = fmin(fmax(uh, 0.0), 32767.0);          // NaN -> 0
     return (0x8000u | (unsigned)(int)ul) | ((0x8000u | (unsigned)(int)uh) << 16);
 }
 // quality[0] / quality[1] (zeroed by the launcher): number of LEAF boxes / sum over them of (half-area as the grid renders the
 // box) / (half-area as stored), each ratio capped at 1000 -- the host keeps the compressed copy only while the mean ratio stays
-// close to 1 (a scene whose detail is finer than a grid cell would enter many more leaves).
+// close to 1 (a scene whose detail is finer than a grid cell would enter many more leaves).  quality[2] != 0: some plane did
+// not fit the grid.
 __device__ __forceinline__ double qplane_value(unsigned s16, float g0, float e) { return (double)g0 + (double)(s16 & 0x7fffu) * (1.0 / 32768.0) * (double)e; }
 __global__ void __launch_bounds__(256)
 k_quantize_pairs(const float4* __restrict__ nodes, int n_pairs, uint4* __restrict__ out, float* __restrict__ grid, double* __restrict__ quality) {
@@ -904,6 +908,7 @@ k_quantize_pairs(const float4* __restrict__ nodes, int n_pairs, uint4* __restric
         for (int c = 0; c < 3; ++c) { grid[c] = g0[c]; grid[3 + c] = e[c]; }
     }
     double area = 0.0, qarea = 0.0;
+    bool out_of_range = false;
     for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < n_pairs; m += gridDim.x * blockDim.x) {
         float lo[3], hi[3];
         int code[2];
@@ -912,7 +917,9 @@ k_quantize_pairs(const float4* __restrict__ nodes, int n_pairs, uint4* __restric
             node_read(nodes, 2 * m + side, lo, hi, code[side]);
             double d[3], q[3];
             for (int c = 0; c < 3; ++c) {
-                const unsigned ww = quantise_axis(lo[c], hi[c], g0[c], e[c]);
+                bool oor = false;
+                const unsigned ww = quantise_axis(lo[c], hi[c], g0[c], e[c], oor);
+                if (oor && !(m == 0 && side == 1)) out_of_range = true;          // (record 1 is the pad record next to the root)
                 w[3 * side + c] = ww;
                 d[c] = (double)hi[c] - (double)lo[c];
                 q[c] = qplane_value(ww >> 16, g0[c], e[c]) - qplane_value(ww & 0xffffu, g0[c], e[c]);
@@ -928,6 +935,7 @@ k_quantize_pairs(const float4* __restrict__ nodes, int n_pairs, uint4* __restric
     }
     for (int o = 16; o > 0; o >>= 1) { area += __shfl_xor_sync(0xffffffffu, area, o); qarea += __shfl_xor_sync(0xffffffffu, qarea, o); }
     if ((threadIdx.x & 31) == 0 && (area != 0.0 || qarea != 0.0)) { atomicAdd(quality, area); atomicAdd(quality + 1, qarea); }
+    if (out_of_range) quality[2] = 1.0;
 }
 // Option "qnodes" bit 1: the 48-byte triangle records as a 32-byte part (v0|prim, e1|material: one 256-bit load) and a 16-byte part (e2|0)
 __global__ void __launch_bounds__(256)
@@ -941,7 +949,7 @@ k_split_tris(const float4* __restrict__ prims, int n, float4* __restrict__ tri_a
 
 cudaError_t launch_quantize_pairs(const float4* d_nodes, int n_pairs, uint4* d_qnodes, float* d_qgrid, double* d_quality, cudaStream_t stream) {
     if (n_pairs <= 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(d_quality, 0, 2 * sizeof(double), stream);
+    cudaError_t e = cudaMemsetAsync(d_quality, 0, 3 * sizeof(double), stream);
     if (e != cudaSuccess) return e;
     k_quantize_pairs<<<elementwise_grid(n_pairs), 256, 0, stream>>>(d_nodes, n_pairs, d_qnodes, d_qgrid, d_quality);
     return cudaGetLastError();

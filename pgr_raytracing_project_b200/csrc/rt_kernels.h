@@ -145,7 +145,8 @@ cudaError_t launch_frame_sync(unsigned long long* words, unsigned long long targ
 cudaError_t launch_build_treelet(const float4* d_nodes, int n_pairs, float4* d_treelet, cudaStream_t stream);
 // Option "qnodes": the tree's sibling pairs compressed to 32 bytes on a 15-bit grid over the root box (d_qgrid: 6 floats), and the
 // triangle records split into a 32-byte and a 16-byte part (rt_device.cuh pair_hit_q, trav_run QM).
-// d_quality[0], [1]: number of leaves, sum of their (half-area on the grid / half-area as stored) (the host's keep-or-drop figure).
+// d_quality[0], [1]: number of leaves, sum of their (half-area on the grid / half-area as stored) (the host's keep-or-drop figure);
+// [2] != 0: a plane did not fit the grid (a child box outside the root box: the compressed copy must not be used).
 cudaError_t launch_quantize_pairs(const float4* d_nodes, int n_pairs, uint4* d_qnodes, float* d_qgrid, double* d_quality, cudaStream_t stream);
 cudaError_t launch_split_tris(const float4* d_prims, int n, float4* d_tri_a, float4* d_tri_b, cudaStream_t stream);
 // rt_render_tiles_host: this launch's 32x32 tiles of the device frame `fb` stored into the page-locked frame `host` (device

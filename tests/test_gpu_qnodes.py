@@ -130,3 +130,27 @@ def test_qnodes_auto_keeps_the_copy_only_on_a_fine_enough_grid(ctx):
         assert np.array_equal(a, c)
     finally:
         ctx.set_option("qnodes", -1); ctx.set_option("kernel", -1)
+
+
+def test_qnodes_refuse_a_tree_whose_boxes_leave_the_root_box(ctx):
+    """A caller-supplied tree (rt_set_bvh) may hold a child box that sticks out of the root box; clamping it to the grid would
+    shrink it, so the compressed pairs are dropped for such a tree (forced or auto) and the frame is the full records'."""
+    s = SCENES["tris20k"]()
+    W, H = 128, 80
+    ctx.set_option("kernel", 4)
+    try:
+        ctx.set_scene(s); ctx.set_camera_array(s.camera.as_array(W / H))
+        ctx.set_option("qnodes", 0)
+        ref = ctx.render(W, H, 2, 4, seed=8).cpu().numpy()
+        nodes, prim_index = ctx.get_bvh()
+        leaf = int(np.flatnonzero((nodes["b"] > 0) & (np.arange(len(nodes)) > 1))[5])
+        nodes = nodes.copy()
+        nodes[leaf]["bmax"] = nodes[leaf]["bmax"] + np.float32(1000.0)          # conservative for the leaf, far outside the root box
+        ctx.set_bvh(nodes, prim_index)
+        for q in (-1, 1, 5):
+            ctx.set_option("qnodes", q)
+            img = ctx.render(W, H, 2, 4, seed=8).cpu().numpy()
+            assert ctx.get_option("qnodes_used") & 1 == 0 and ctx.get_option("qnodes_area_pct") == -1, q
+            assert np.array_equal(img, ref), q
+    finally:
+        ctx.set_option("qnodes", -1); ctx.set_option("kernel", -1)
