@@ -127,3 +127,19 @@ def test_sah_million_triangle_build_time():
     dt = time.time() - t0
     assert len(index) == 1_000_000 and len(nodes) > 500_000
     assert dt < 60.0, f"SAH host build of 1M triangles took {dt:.1f}s"
+
+
+def test_host_builder_ex_rejects_bad_arguments():
+    """rt_build_bvh_host_ex: the device builder (1) needs a context, leaf sizes are 1..4 -- errors, with a message, not a guess."""
+    from pgr_raytracing_project_b200 import _lib
+    from pgr_raytracing_project_b200.context import B200RTError
+    tri = scenes.random_triangles(10, seed=1).vertices
+    for builder, leaf in ((1, 4), (3, 4), (-1, 4), (0, 0), (2, 5)):
+        with pytest.raises(B200RTError):
+            build_bvh_host(tri, True, builder=builder, leaf_size=leaf)
+        assert b"rt_build_bvh_host_ex" in _lib.load().rt_last_error(None)
+    for leaf in (1, 2, 3, 4):                     # every legal leaf size, both host builders: leaves within the bound, all primitives covered
+        for builder in (0, 2):
+            nodes, index = build_bvh_host(scenes.random_triangles(500, seed=2).vertices, True, builder=builder, leaf_size=leaf)
+            leaves = nodes["b"][(nodes["b"] > 0) & (np.arange(len(nodes)) != 1)]
+            assert leaves.max() <= leaf and leaves.sum() == 500 and sorted(index.tolist()) == list(range(500))
